@@ -1,0 +1,193 @@
+/*
+ * gssd.h — C ABI of the B200-native GSSD multibox head (libgssd_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of L0SG/grouped-ssd-pytorch:
+ *   PriorBox -> match/encode -> MultiBoxLoss (OHNM) -> Detect (decode / threshold / top-k / NMS)
+ * The reference has no FFI of its own: the boundary that exists there is the Python package
+ * `ssd_liverdet/layers` (layers/__init__.py:1-2).  Each entry point below names the reference
+ * function it replaces (paths relative to /root/reference/ssd_liverdet/).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller (PyTorch's caching allocator, in the shipped host layer) owns every buffer,
+ *     including the workspace; nothing is allocated, freed or synchronised in here, so every
+ *     call is legal inside CUDA-graph capture;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value: 0 on success, a negative GSSD_ERR_* for argument errors (checked before any
+ *     launch), or a positive cudaError_t if a launch failed;
+ *   - boxes are float32; "center form" = (cx,cy,w,h), "point form" = (xmin,ymin,xmax,ymax);
+ *   - ground truth is packed: gt[sum_G,5] rows (xmin,ymin,xmax,ymax,label) and gt_off[B+1]
+ *     int32 row offsets (image b owns rows gt_off[b]..gt_off[b+1]), the device-side image of the
+ *     reference's `targets` list (multibox_loss.py:67-69);
+ *   - float arithmetic is IEEE, unfused (no FMA contraction), in the reference's association order.
+ */
+#ifndef GSSD_H_
+#define GSSD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSSD_ABI_VERSION 1
+
+#define GSSD_OK          0
+#define GSSD_ERR_ARG    -1   /* null pointer / non-positive size / bad enum */
+#define GSSD_ERR_LIMIT  -2   /* size beyond what the kernels support (see GSSD_MAX_*) */
+#define GSSD_ERR_WS     -3   /* workspace smaller than gssd_workspace_bytes() */
+#define GSSD_ERR_VALUE  -4   /* reference-visible ValueError (variance <= 0, nms_thresh <= 0) */
+#define GSSD_ERR_EMPTY  -5   /* an image without ground truth (reference: IndexError) */
+
+#define GSSD_MAX_GT_PER_IMAGE   128    /* G per image held in shared memory */
+#define GSSD_MAX_PRIORS       49152    /* P: keys of one image must fit one SM's shared memory */
+#define GSSD_MAX_TOP_K         1024
+#define GSSD_MAX_CLASSES         64
+#define GSSD_MAX_FEATURE_MAPS     8
+#define GSSD_MAX_ASPECT_RATIOS    8
+
+int         gssd_abi_version(void);
+const char *gssd_error_string(int code);
+/* number of kernels launched by this library since load (bench.py's gpu_launches claim) */
+uint64_t    gssd_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * PriorBox — replaces PriorBox.__init__/forward, layers/functions/prior_box.py:14-172
+ * ---------------------------------------------------------------------------------------- */
+enum {
+    GSSD_PRIOR_V2 = 0,             /* 'v2' and 'v2_512' : prior_box.py:35-56, 116-138 */
+    GSSD_PRIOR_V2_CUSTOM = 1,      /* 'v2_custom', 'v2_custom_squareonly', 'v2_custom_512': 58-114 */
+    GSSD_PRIOR_LEGACY = 2          /* any other name (e.g. 'v1'), corner form: 141-167 */
+};
+
+typedef struct gssd_prior_cfg {
+    int32_t version;                                   /* GSSD_PRIOR_* */
+    int32_t n_maps;                                    /* len(cfg['feature_maps']) */
+    int32_t clip;                                      /* cfg['clip'] */
+    int32_t feature_maps[GSSD_MAX_FEATURE_MAPS];
+    int32_t n_ar[GSSD_MAX_FEATURE_MAPS];               /* len(cfg['aspect_ratios'][k]) */
+    double  min_dim;                                   /* cfg['min_dim'] */
+    double  steps[GSSD_MAX_FEATURE_MAPS];
+    double  min_sizes[GSSD_MAX_FEATURE_MAPS];
+    double  max_sizes[GSSD_MAX_FEATURE_MAPS];
+    double  aspect_ratios[GSSD_MAX_FEATURE_MAPS][GSSD_MAX_ASPECT_RATIOS];
+    double  variance[2];                               /* validated > 0 (prior_box.py:28-30) */
+} gssd_prior_cfg;
+
+/* host-only: number of boxes P the config generates, or a negative GSSD_ERR_* */
+int gssd_priorbox_count(const gssd_prior_cfg *cfg_host);
+/* out[P,4] float32.  fp64 arithmetic in the reference's order, one rounding to fp32, then clamp. */
+int gssd_priorbox(const gssd_prior_cfg *cfg_host, float *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * box_utils — replaces layers/box_utils.py
+ * ---------------------------------------------------------------------------------------- */
+/* point_form, box_utils.py:4-13 : (cx,cy,w,h) -> (xmin,ymin,xmax,ymax), [n,4] -> [n,4] */
+int gssd_point_form(const float *boxes, int n, float *out, void *stream);
+/* center_size, box_utils.py:16-25 (documented intent; the reference body is malformed) */
+int gssd_center_size(const float *boxes, int n, float *out, void *stream);
+/* intersect, box_utils.py:28-46 : a[A,4], b[Bn,4] point form -> out[A,Bn] */
+int gssd_intersect(const float *a, int A, const float *b, int Bn, float *out, void *stream);
+/* jaccard, box_utils.py:49-67 : IoU matrix out[A,Bn]; union = (area_a + area_b) - inter */
+int gssd_jaccard(const float *a, int A, const float *b, int Bn, float *out, void *stream);
+/* encode, box_utils.py:114-135 : matched[n,4] point form, priors[n,4] center form -> out[n,4] */
+int gssd_encode(const float *matched, const float *priors, int n, float var0, float var1,
+                float *out, void *stream);
+/* decode, box_utils.py:139-157 : loc[n,4], priors[n,4] -> out[n,4] point form (not clipped) */
+int gssd_decode(const float *loc, const float *priors, int n, float var0, float var1,
+                float *out, void *stream);
+/* log_sum_exp, box_utils.py:160-168 : x[rows,C] -> out[rows]; subtracts the max of the WHOLE
+ * tensor.  ws: gssd_workspace_bytes(GSSD_WS_LSE, ...) */
+int gssd_log_sum_exp(const float *x, int rows, int C, float *out, void *ws, size_t ws_bytes,
+                     void *stream);
+
+/* match, box_utils.py:70-111, batched over B images (the loop at multibox_loss.py:67-72).
+ *   priors[P,4] center form; gt/gt_off packed ground truth (sum_G rows; g_max = max rows/image);
+ *   loc_t[B,P,4] float32 and conf_t[B,P] int64 are written for every prior (box_utils.py:109-111);
+ *   best_truth_idx[B,P] int32 (optional, may be NULL) = final matched GT row within the image.
+ * Ties: argmax -> lowest index; shared best prior -> highest GT row wins (box_utils.py:104-105). */
+int gssd_match(const float *priors, int P, const float *gt, const int32_t *gt_off, int B,
+               int sum_G, int g_max, float threshold, float var0, float var1,
+               float *loc_t, int64_t *conf_t, int32_t *best_truth_idx,
+               void *ws, size_t ws_bytes, void *stream);
+
+/* nms, box_utils.py:174-238 : boxes[n,4] point form, scores[n].
+ *   keep[n] int64 zero-padded, count[1] int32 (device).  Candidates are the top_k scores BEFORE
+ *   suppression; union = (area_j - inter) + area_i; kept iff IoU <= overlap.
+ *   Equal scores: higher index first (stable ascending sort read from the end). */
+int gssd_nms(const float *boxes, const float *scores, int n, float overlap, int top_k,
+             int64_t *keep, int32_t *count, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * MultiBoxLoss — replaces MultiBoxLoss.forward, layers/modules/multibox_loss.py:46-120, and the
+ * autograd backward of its two outputs.  Two stages so that a multi-GPU host can all-reduce the
+ * two batch-global scalars between them (stats[0] = max of conf as float bits, MAX;
+ * stats[1] = number of positives N as int32, SUM).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct gssd_loss_stats {     /* device-resident, 16 bytes */
+    float   conf_max;                /* x_max of log_sum_exp (box_utils.py:167), whole local batch */
+    int32_t num_pos_total;           /* N (multibox_loss.py:117) */
+    int32_t reserved[2];
+} gssd_loss_stats;
+
+/* Stage 1: matching (box_utils.py:70-108) + batch max of conf.
+ *   tags[B,P] uint16 : bit15 = positive, bits0-14 = matched GT row within the image
+ *   num_pos[B] int32, stats (zero-initialised by this call). */
+int gssd_mbox_match(const float *priors, int P, const float *conf, int C,
+                    const float *gt, const int32_t *gt_off, int B, int sum_G, int g_max,
+                    float threshold, uint16_t *tags, int32_t *num_pos, gssd_loss_stats *stats,
+                    void *stream);
+
+/* Stage 2: encode + smooth-L1 (multibox_loss.py:80-88), mining key with the global-max LSE
+ * (91-101), hard-negative selection of min(negpos_ratio*num_pos, P-1) keys per image (102-106;
+ * descending key, ties -> lower prior index), cross-entropy over pos|neg (108-113), division by N
+ * (117-119) and the gradients of both losses.
+ *   losses[2] float32 = (loss_l/N, loss_c/N);  grad_loc[B,P,4], grad_conf[B,P,C] = d(loss_l)/d(loc),
+ *   d(loss_c)/d(conf) (NULL, NULL for forward only); pos_mask/neg_mask[B,P] uint8 optional. */
+int gssd_mbox_loss(const float *loc, const float *conf, const float *priors, int B, int P, int C,
+                   const float *gt, const int32_t *gt_off, int sum_G, int g_max,
+                   const uint16_t *tags, const int32_t *num_pos, const gssd_loss_stats *stats,
+                   int negpos_ratio, float var0, float var1,
+                   float *losses, float *grad_loc, float *grad_conf,
+                   uint8_t *pos_mask, uint8_t *neg_mask,
+                   void *ws, size_t ws_bytes, void *stream);
+
+/* Backward helper: grad_loc *= g[0], grad_conf *= g[1] in place (g = upstream gradients of the two
+ * scalar losses, device).  Touches no memory when g == (1,1), the `(loss_l+loss_c).backward()` case
+ * of train_lesion_multiphase_v2.py:247-248. */
+int gssd_mbox_scale_grads(float *grad_loc, size_t n_loc, float *grad_conf, size_t n_conf,
+                          const float *g_loc, const float *g_conf, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Detect — replaces Detect.forward, layers/functions/detection_pytorch_ver_1point5.py:33-89
+ * (and the legacy detection.py:13-62).
+ *   loc[B,P,4], conf[B,P,C] (already softmaxed), priors[P,4]
+ *   out[B,C,top_k,5] rows (score,xmin,ymin,xmax,ymax) in descending score, zero-padded; class 0
+ *   slab is all zero; count[B,C] int32 and keep_idx[B,C,top_k] int32 (prior index, -1 padded) are
+ *   optional (may be NULL). */
+int gssd_detect(const float *loc, const float *conf, const float *priors, int B, int P, int C,
+                int top_k, float conf_thresh, float nms_thresh, float var0, float var1,
+                float *out, int32_t *count, int32_t *keep_idx, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * L2Norm — replaces L2Norm.forward, layers/modules/l2norm.py:19-23, and its backward.
+ *   x[B,Cn,HW] (NCHW), weight[Cn]; y = weight[c] * x / (sqrt(sum_c x^2) + eps)
+ * ---------------------------------------------------------------------------------------- */
+int gssd_l2norm_fwd(const float *x, const float *weight, int B, int Cn, int HW, float eps,
+                    float *y, float *norm /* [B,HW], saved for backward, may be NULL */, void *stream);
+int gssd_l2norm_bwd(const float *x, const float *weight, const float *norm, const float *gy,
+                    int B, int Cn, int HW, float eps, float *gx,
+                    float *gw_partial /* [n_partial,Cn] */, int n_partial, void *stream);
+int gssd_l2norm_bwd_partials(int B, int Cn, int HW);
+
+/* ------------------------------------------------------------------------------------------
+ * workspace sizing (host-only)
+ * ---------------------------------------------------------------------------------------- */
+enum { GSSD_WS_LSE = 0, GSSD_WS_MATCH = 1, GSSD_WS_LOSS = 2, GSSD_WS_NMS = 3 };
+size_t gssd_workspace_bytes(int kind, int B, int P, int C, int sum_G, int top_k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSSD_H_ */

@@ -1,0 +1,89 @@
+"""Seeded inputs shared by the golden generator (tests/golden/make_golden.py), the oracle tests and
+the GPU parity tests.  Everything here is regenerated from seeds with frozen numpy streams."""
+import os
+
+import numpy as np
+
+from grouped_ssd_pytorch_b200 import config as cfg
+from grouped_ssd_pytorch_b200 import synthetic as syn
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+VAR = (0.1, 0.2)
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def small_cfg():
+    c = dict(cfg.v2)
+    c.update(feature_maps=[5, 3, 1], steps=[60, 100, 300], min_sizes=[60, 150, 240],
+             max_sizes=[150, 240, 315], aspect_ratios=[[2], [2, 3], [2]])
+    return c
+
+
+def priors(name):
+    """golden prior set by name (reference output)."""
+    return golden("priors")[name]
+
+
+def match_rand_targets():
+    return syn.targets(syn.rng(11), 3, 1, 5)
+
+
+def loss_case(tag):
+    """-> (loc, conf, priors, targets, num_classes, ratio)"""
+    if tag == "a":
+        pri = priors("v2"); r = syn.rng(21)
+        tg = syn.targets(r, 4, 1, 5)
+        return syn.loc(r, 4, pri.shape[0]), syn.conf_logits(r, 4, pri.shape[0], 2), pri, tg, 2, 3
+    if tag == "b":
+        pri = priors("v2"); r = syn.rng(22)
+        tg = syn.targets(r, 3, 1, 8)
+        for t in tg:
+            t[:, 4] = r.randint(0, 2, size=t.shape[0])
+        return syn.loc(r, 3, pri.shape[0]), syn.conf_logits(r, 3, pri.shape[0], 3) * 2, pri, tg, 3, 2
+    if tag == "c":
+        pri = priors("small"); r = syn.rng(23)
+        tg = syn.targets(r, 2, 60, 64)
+        return syn.loc(r, 2, pri.shape[0]), syn.conf_logits(r, 2, pri.shape[0], 2), pri, tg, 2, 4
+    if tag == "d":
+        pri = priors("v2_512"); r = syn.rng(24)
+        tg = syn.targets(r, 2, 1, 32)
+        return syn.loc(r, 2, pri.shape[0]), syn.conf_logits(r, 2, pri.shape[0], 2), pri, tg, 2, 3
+    raise KeyError(tag)
+
+
+def detect_case(tag):
+    """-> (loc, conf, priors, C, thr)"""
+    pri = priors("v2")
+    P = pri.shape[0]
+    table = {"a": (41, 2, 2, -4.0, 0.5, 0.2), "b": (42, 2, 2, 0.0, 0.05, 0.2), "c": (43, 1, 3, -3.0, 0.2, 0.01),
+             "d": (44, 1, 2, -30.0, 0.5, 0.2)}
+    seed, B, C, shift, sigma, thr = table[tag]
+    r = syn.rng(seed)
+    loc = syn.loc(r, B, P, sigma)
+    conf = syn.detect_scores(r, B, P, C, shift)
+    return loc, conf, pri, C, thr
+
+
+def dense_grads(g, prefix, shape):
+    out = np.zeros(int(np.prod(shape)), np.float32)
+    out[g[prefix + "_idx"]] = g[prefix + "_val"]
+    return out.reshape(shape)
+
+
+def ohnm_unambiguous(key, pos, ratio):
+    """per image: is the reference's pos|neg set independent of how its unstable sort orders equal keys?
+    True when no key tie straddles the num_neg cut, or when every prior tied there is a positive
+    (positives are in the union anyway)."""
+    B, P = key.shape
+    ok = np.zeros(B, bool)
+    for b in range(B):
+        nn = min(ratio * int(pos[b].sum()), P - 1)
+        ks = np.sort(key[b])[::-1]
+        if nn <= 0 or nn >= P or ks[nn - 1] != ks[nn]:
+            ok[b] = True
+        else:
+            ok[b] = bool(pos[b][key[b] == ks[nn]].all())
+    return ok
