@@ -1,0 +1,154 @@
+"""ctypes binding of libgssd_b200.so (include/gssd.h).  No CPU fallback: if the library cannot be
+loaded or no CUDA device is present, every entry point raises."""
+import ctypes as C
+import os
+
+import torch
+
+from . import build as _build
+
+ERR_ARG, ERR_LIMIT, ERR_WS, ERR_VALUE, ERR_EMPTY = -1, -2, -3, -4, -5
+MAX_MAPS, MAX_AR = 8, 8
+PRIOR_V2, PRIOR_V2_CUSTOM, PRIOR_LEGACY = 0, 1, 2
+WS_LSE, WS_MATCH, WS_LOSS, WS_NMS = 0, 1, 2, 3
+STATS_HEADER_BYTES = 16
+
+
+class PriorCfg(C.Structure):
+    """`gssd_prior_cfg` (include/gssd.h)."""
+    _fields_ = [
+        ("version", C.c_int32), ("n_maps", C.c_int32), ("clip", C.c_int32),
+        ("feature_maps", C.c_int32 * MAX_MAPS), ("n_ar", C.c_int32 * MAX_MAPS),
+        ("min_dim", C.c_double), ("steps", C.c_double * MAX_MAPS),
+        ("min_sizes", C.c_double * MAX_MAPS), ("max_sizes", C.c_double * MAX_MAPS),
+        ("aspect_ratios", (C.c_double * MAX_AR) * MAX_MAPS), ("variance", C.c_double * 2),
+    ]
+
+
+_P, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_SIGS = {
+    "gssd_abi_version": (C.c_int, []),
+    "gssd_error_string": (C.c_char_p, [_I]),
+    "gssd_launch_count": (C.c_uint64, []),
+    "gssd_priorbox_count": (_I, [C.POINTER(PriorCfg)]),
+    "gssd_priorbox": (_I, [C.POINTER(PriorCfg), _P, _P]),
+    "gssd_point_form": (_I, [_P, _I, _P, _P]),
+    "gssd_center_size": (_I, [_P, _I, _P, _P]),
+    "gssd_intersect": (_I, [_P, _I, _P, _I, _P, _P]),
+    "gssd_jaccard": (_I, [_P, _I, _P, _I, _P, _P]),
+    "gssd_encode": (_I, [_P, _P, _I, _F, _F, _P, _P]),
+    "gssd_decode": (_I, [_P, _P, _I, _F, _F, _P, _P]),
+    "gssd_log_sum_exp": (_I, [_P, _I, _I, _P, _P, _SZ, _P]),
+    "gssd_match": (_I, [_P, _I, _P, _P, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _SZ, _P]),
+    "gssd_nms": (_I, [_P, _P, _I, _F, _I, _P, _P, _P, _SZ, _P]),
+    "gssd_stats_bytes": (_SZ, [_I]),
+    "gssd_mbox_match": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _F, _P, _P, _P]),
+    "gssd_mbox_loss": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _I, _I, _F, _F,
+                            _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "gssd_mbox_scale_grads": (_I, [_P, _SZ, _P, _SZ, _P, _P, _P]),
+    "gssd_detect": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P]),
+    "gssd_l2norm_fwd": (_I, [_P, _P, _I, _I, _I, _F, _P, _P, _P]),
+    "gssd_l2norm_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _SZ, _P]),
+    "gssd_l2norm_bwd_ws_bytes": (_SZ, [_I, _I, _I]),
+    "gssd_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library (building it first when the sources are newer and nvcc exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if _build.stale():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on this box and no prebuilt library
+            if not os.path.exists(path):
+                raise RuntimeError("libgssd_b200.so is missing and could not be built: %s" % e)
+    lib = C.CDLL(path)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if lib.gssd_abi_version() != 1:
+        raise RuntimeError("libgssd_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("grouped_ssd_pytorch_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return load()
+
+
+def check(rc, what=""):
+    if rc == 0:
+        return
+    msg = load().gssd_error_string(rc).decode()
+    if rc == ERR_VALUE:
+        raise ValueError(what or msg)
+    if rc == ERR_EMPTY:
+        raise IndexError(what or msg)
+    raise RuntimeError("%s: %s (code %d)" % (what or "libgssd_b200", msg, rc))
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def device_of(*tensors):
+    """the CUDA device to compute on: the first CUDA tensor's, else the current device."""
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            return t.device
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def f32(t, dev):
+    """contiguous float32 view/copy of `t` on `dev` (no copy when it already is)."""
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def launch_count():
+    return int(load().gssd_launch_count())
+
+
+def prior_cfg(cfg):
+    """cfg dict -> PriorCfg; branch selection follows prior_box.py:35,58,87,116,139."""
+    c = PriorCfg()
+    name = cfg["name"]
+    if name in ("v2", "v2_512"):
+        c.version = PRIOR_V2
+    elif name in ("v2_custom", "v2_custom_squareonly", "v2_custom_512"):
+        c.version = PRIOR_V2_CUSTOM
+    else:
+        c.version = PRIOR_LEGACY
+    c.n_maps = len(cfg["feature_maps"])
+    if c.n_maps > MAX_MAPS:
+        raise RuntimeError("PriorBox: more than %d feature maps" % MAX_MAPS)
+    c.clip = 1 if cfg["clip"] else 0
+    c.min_dim = float(cfg["min_dim"])
+    for k in range(c.n_maps):
+        c.feature_maps[k] = int(cfg["feature_maps"][k])
+        c.steps[k] = float(cfg["steps"][k])
+        c.min_sizes[k] = float(cfg["min_sizes"][k])
+        c.max_sizes[k] = float(cfg["max_sizes"][k])
+        ars = cfg["aspect_ratios"][k]
+        if len(ars) > MAX_AR:
+            raise RuntimeError("PriorBox: more than %d aspect ratios" % MAX_AR)
+        c.n_ar[k] = len(ars)
+        for a, ar in enumerate(ars):
+            c.aspect_ratios[k][a] = float(ar)
+    var = cfg["variance"] or [0.1]
+    c.variance[0] = float(var[0])
+    c.variance[1] = float(var[-1])
+    return c

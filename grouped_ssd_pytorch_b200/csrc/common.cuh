@@ -1,0 +1,118 @@
+// common.cuh — shared device helpers for libgssd_b200.so (sm_100a).
+//
+// Arithmetic contract: every float operation that feeds a discrete decision (IoU, thresholds, mining
+// keys, decoded boxes) is an IEEE round-to-nearest add/sub/mul/div in the reference's association
+// order.  The library is compiled with -fmad=false and the hot expressions additionally use the
+// __f*_rn intrinsics, which ptxas never contracts into FMA.
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gssd.h"
+
+namespace cg = cooperative_groups;
+
+namespace gssd {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// host-side launch accounting (gssd_launch_count)
+void note_launch(int n = 1);
+
+#define GSSD_RETURN_IF_CUDA(expr)                          \
+    do {                                                   \
+        cudaError_t _e = (expr);                           \
+        if (_e != cudaSuccess) return (int)_e;             \
+    } while (0)
+
+#define GSSD_AFTER_LAUNCH()                                \
+    do {                                                   \
+        gssd::note_launch();                               \
+        cudaError_t _e = cudaPeekAtLastError();            \
+        if (_e != cudaSuccess) return (int)_e;             \
+    } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- order-preserving float <-> uint32 (larger float <=> larger unsigned) -----------------------
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// ---- box arithmetic -------------------------------------------------------------------------------
+// point_form, box_utils.py:4-13 : c -/+ wh/2 (the /2 is exact)
+__device__ __forceinline__ float4 point_form(float4 p) {
+    float hw = __fmul_rn(p.z, 0.5f), hh = __fmul_rn(p.w, 0.5f);
+    return make_float4(__fsub_rn(p.x, hw), __fsub_rn(p.y, hh), __fadd_rn(p.x, hw), __fadd_rn(p.y, hh));
+}
+__device__ __forceinline__ float box_area(float4 b) {
+    return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+// intersect, box_utils.py:28-46
+__device__ __forceinline__ float box_inter(float4 a, float4 b) {
+    float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+    float h = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+    w = w < 0.f ? 0.f : w;          // torch.clamp(min=0)
+    h = h < 0.f ? 0.f : h;
+    return __fmul_rn(w, h);
+}
+// jaccard, box_utils.py:49-67 : inter / ((area_a + area_b) - inter)
+__device__ __forceinline__ float box_iou_exact(float4 a, float area_a, float4 b, float area_b) {
+    float inter = box_inter(a, b);
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+}
+// Same value whenever the union is positive (always, for priors of positive area): the IEEE divide is
+// skipped for the disjoint pairs, which are the vast majority of (GT, prior) pairs.
+__device__ __forceinline__ float box_iou_fast(float4 a, float area_a, float4 b, float area_b) {
+    float inter = box_inter(a, b);
+    if (!(inter > 0.f)) return 0.f;
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+}
+// encode, box_utils.py:114-135 (true divisions, as the reference's CPU path)
+__device__ __forceinline__ float4 encode_box(float4 m, float4 p, float v0, float v1) {
+    float4 o;
+    o.x = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(m.x, m.z), 0.5f), p.x), __fmul_rn(v0, p.z));
+    o.y = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(m.y, m.w), 0.5f), p.y), __fmul_rn(v0, p.w));
+    o.z = __fdiv_rn(logf(__fdiv_rn(__fsub_rn(m.z, m.x), p.z)), v1);
+    o.w = __fdiv_rn(logf(__fdiv_rn(__fsub_rn(m.w, m.y), p.w)), v1);
+    return o;
+}
+// decode, box_utils.py:139-157
+__device__ __forceinline__ float4 decode_box(float4 l, float4 p, float v0, float v1) {
+    float cx = __fadd_rn(p.x, __fmul_rn(__fmul_rn(l.x, v0), p.z));
+    float cy = __fadd_rn(p.y, __fmul_rn(__fmul_rn(l.y, v0), p.w));
+    float w = __fmul_rn(p.z, expf(__fmul_rn(l.z, v1)));
+    float h = __fmul_rn(p.w, expf(__fmul_rn(l.w, v1)));
+    cx = __fsub_rn(cx, __fmul_rn(w, 0.5f));
+    cy = __fsub_rn(cy, __fmul_rn(h, 0.5f));
+    return make_float4(cx, cy, __fadd_rn(w, cx), __fadd_rn(h, cy));
+}
+
+// ---- warp / block reductions ---------------------------------------------------------------------
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// streaming (read-once) loads: keep them out of L1
+__device__ __forceinline__ float4 ldg_stream(const float4 *p) { return __ldcs(p); }
+__device__ __forceinline__ float2 ldg_stream(const float2 *p) { return __ldcs(p); }
+__device__ __forceinline__ float ldg_stream(const float *p) { return __ldcs(p); }
+
+}  // namespace gssd

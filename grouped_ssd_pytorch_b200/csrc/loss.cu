@@ -1,0 +1,301 @@
+// loss.cu — stage 2 of MultiBoxLoss (multibox_loss.py:80-120) with its backward fused in.
+//
+// One thread-block cluster per image, contiguous prior slices per CTA.
+//   sweep 1: tag (2 B) + conf row per prior; positives also read loc + prior, encode their target on
+//            the fly (box_utils.py:114-135; never materialised), add smooth-L1 and emit d(loss_l)/d(loc);
+//            every prior gets its mining key log(sum exp(x - x_max)) + x_max - x[0] with the
+//            BATCH-GLOBAL x_max (box_utils.py:160-168, multibox_loss.py:91-99) as an ordered uint32 in
+//            shared memory;
+//   select : radix select of the min(ratio*num_pos, P-1) largest keys (select.cuh) — replaces the two
+//            full sorts of multibox_loss.py:102-103;
+//   sweep 2: cross-entropy (torch log_softmax, row max) over pos|neg and d(loss_c)/d(conf), zeros
+//            elsewhere; conf is re-read from L1/L2;
+//   finish : per-CTA partial sums in double, the last CTA reduces them in a fixed order and divides
+//            by N (multibox_loss.py:117-119).
+#include "select.cuh"
+
+namespace gssd {
+
+constexpr int LOSS_NT = 256;
+
+struct LossArgs {
+    const float4 *loc; const float *conf; const float4 *priors;
+    int B, P, C;
+    const float *gt; const int32_t *gt_off;
+    const uint16_t *tags;
+    uint32_t *stats;                        // local stats_buf (header + num_pos[B])
+    const uint32_t *gstats; int n_gstats;   // headers of all ranks (or null)
+    int ratio; float var0, var1;
+    float *losses; float4 *grad_loc; float *grad_conf;
+    uint8_t *pos_mask, *neg_mask;
+    double *partials;                       // [2 * n_ctas]
+    int slice;
+};
+
+__device__ __forceinline__ float smooth_l1(float d, float &grad) {
+    float ad = fabsf(d);
+    if (ad < 1.f) { grad = d; return __fmul_rn(__fmul_rn(0.5f, d), d); }
+    grad = d > 0.f ? 1.f : -1.f;
+    return __fsub_rn(ad, 0.5f);
+}
+
+// C2: num_classes == 2 fast path (float2 rows)
+template <bool C2, bool CLUSTER, bool GRADS>
+__global__ void __launch_bounds__(LOSS_NT) loss_kernel(LossArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ SelectShared sel_s;
+    __shared__ double s_red[2][LOSS_NT / 32];
+    __shared__ bool s_last;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = CLUSTER ? cluster.block_rank() : 0;
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g0 = a.gt_off[b];
+    const int G = a.gt_off[b + 1] - g0;
+    const int C = C2 ? 2 : a.C;
+
+    float *sgt = reinterpret_cast<float *>(smem_raw);                    // [G][5]
+    uint32_t *keys = reinterpret_cast<uint32_t *>(sgt + 5 * ((G + 3) & ~3));
+    for (int i = tid; i < 5 * G; i += LOSS_NT) sgt[i] = a.gt[5 * (size_t)g0 + i];
+
+    // batch-global scalars: max over ranks of x_max, sum over ranks of N
+    float x_max; int n_total;
+    {
+        uint32_t mo = a.stats[0]; int nt = (int)a.stats[1];
+        if (a.gstats) {
+            mo = 0; nt = 0;
+            for (int r = 0; r < a.n_gstats; ++r) { mo = max(mo, a.gstats[4 * r]); nt += (int)a.gstats[4 * r + 1]; }
+        }
+        x_max = ord2f(mo); n_total = nt;
+    }
+    const float n_f = (float)n_total;
+    const int num_pos = reinterpret_cast<const int *>(a.stats + 4)[b];
+    __syncthreads();
+
+    const int p0 = rank * a.slice;
+    const int p1 = min(a.P, p0 + a.slice);
+    const int n_local = max(p1 - p0, 0);
+    double acc_l = 0.0, acc_c = 0.0;
+
+    // ---- sweep 1 ---------------------------------------------------------------------------------
+    for (int p = p0 + tid; p < p1; p += LOSS_NT) {
+        const size_t o = (size_t)b * a.P + p;
+        const uint16_t tag = a.tags[o];
+        const bool pos = tag & 0x8000;
+        const float *row = a.conf + o * C;
+        float key;
+        if (C2) {
+            float2 x = *reinterpret_cast<const float2 *>(row);
+            float s = __fadd_rn(expf(__fsub_rn(x.x, x_max)), expf(__fsub_rn(x.y, x_max)));
+            key = __fsub_rn(__fadd_rn(logf(s), x_max), x.x);
+        } else {
+            float s = 0.f;
+            for (int c = 0; c < C; ++c) s = __fadd_rn(s, expf(__fsub_rn(row[c], x_max)));
+            key = __fsub_rn(__fadd_rn(logf(s), x_max), row[0]);
+        }
+        key = pos ? 0.f : __fadd_rn(key, 0.f);               // loss_c[pos] = 0 ; -0 -> +0
+        keys[p - p0] = f2ord(key);
+        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pos) {
+            const float *t = sgt + 5 * (tag & 0x7fff);
+            float4 lt = encode_box(make_float4(t[0], t[1], t[2], t[3]), a.priors[p], a.var0, a.var1);
+            float4 l = a.loc[o];
+            float l0 = smooth_l1(__fsub_rn(l.x, lt.x), g4.x), l1 = smooth_l1(__fsub_rn(l.y, lt.y), g4.y);
+            float l2 = smooth_l1(__fsub_rn(l.z, lt.z), g4.z), l3 = smooth_l1(__fsub_rn(l.w, lt.w), g4.w);
+            acc_l += (double)l0 + (double)l1 + (double)l2 + (double)l3;
+            g4.x = __fdiv_rn(g4.x, n_f); g4.y = __fdiv_rn(g4.y, n_f); g4.z = __fdiv_rn(g4.z, n_f); g4.w = __fdiv_rn(g4.w, n_f);
+        }
+        if (GRADS) __stcs(&a.grad_loc[o], g4);
+    }
+    __syncthreads();
+
+    // ---- hard-negative selection (multibox_loss.py:102-106) -----------------------------------------
+    long long k = (long long)a.ratio * num_pos;
+    if (k > a.P - 1) k = a.P - 1;
+    SelectResult sel;
+    sel.v = 0xffffffffu; sel.need = 0; sel.eq = 0; sel.tie_cut = 0; sel.low_first = true;   // selects nothing
+    const bool have_sel = k > 0;
+    if (have_sel) sel = radix_select<LOSS_NT, CLUSTER>(keys, n_local, (uint32_t)k, true, &sel_s);
+
+    // ---- sweep 2 ---------------------------------------------------------------------------------
+    for (int p = p0 + tid; p < p1; p += LOSS_NT) {
+        const size_t o = (size_t)b * a.P + p;
+        const uint16_t tag = a.tags[o];
+        const bool pos = tag & 0x8000;
+        const uint32_t kk = keys[p - p0];
+        const bool neg = have_sel && sel.selected(kk, p - p0);
+        if (a.pos_mask) a.pos_mask[o] = pos;
+        if (a.neg_mask) a.neg_mask[o] = neg;
+        const float *row = a.conf + o * C;
+        const bool on = pos || neg;
+        if (C2) {
+            float2 gz = make_float2(0.f, 0.f);
+            if (on) {
+                float2 x = *reinterpret_cast<const float2 *>(row);
+                int t = pos ? (int)__fadd_rn(sgt[5 * (tag & 0x7fff) + 4], 1.f) : 0;
+                float m = fmaxf(x.x, x.y);
+                float e0 = expf(__fsub_rn(x.x, m)), e1 = expf(__fsub_rn(x.y, m));
+                float ls = logf(__fadd_rn(e0, e1));
+                float xt = t == 0 ? x.x : x.y;
+                acc_c += (double)(-(__fsub_rn(__fsub_rn(xt, m), ls)));
+                gz.x = __fdiv_rn(expf(__fsub_rn(__fsub_rn(x.x, m), ls)) - (t == 0 ? 1.f : 0.f), n_f);
+                gz.y = __fdiv_rn(expf(__fsub_rn(__fsub_rn(x.y, m), ls)) - (t == 1 ? 1.f : 0.f), n_f);
+            }
+            if (GRADS) __stcs(reinterpret_cast<float2 *>(a.grad_conf + o * 2), gz);
+        } else {
+            if (on) {
+                int t = pos ? (int)__fadd_rn(sgt[5 * (tag & 0x7fff) + 4], 1.f) : 0;
+                float m = row[0];
+                for (int c = 1; c < C; ++c) m = fmaxf(m, row[c]);
+                float s = 0.f;
+                for (int c = 0; c < C; ++c) s = __fadd_rn(s, expf(__fsub_rn(row[c], m)));
+                float ls = logf(s);
+                float xt = (t >= 0 && t < C) ? row[t] : row[0];
+                acc_c += (double)(-(__fsub_rn(__fsub_rn(xt, m), ls)));
+                if (GRADS)
+                    for (int c = 0; c < C; ++c)
+                        a.grad_conf[o * C + c] = __fdiv_rn(expf(__fsub_rn(__fsub_rn(row[c], m), ls)) - (c == t ? 1.f : 0.f), n_f);
+            } else if (GRADS) {
+                for (int c = 0; c < C; ++c) a.grad_conf[o * C + c] = 0.f;
+            }
+        }
+    }
+
+    // ---- finish ----------------------------------------------------------------------------------
+    acc_l = warp_sum(acc_l); acc_c = warp_sum(acc_c);
+    if (lane == 0) { s_red[0][warp] = acc_l; s_red[1][warp] = acc_c; }
+    __syncthreads();
+    const unsigned n_ctas = gridDim.x * gridDim.y;
+    const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
+    if (tid == 0) {
+        double l = 0.0, c = 0.0;
+        for (int w = 0; w < LOSS_NT / 32; ++w) { l += s_red[0][w]; c += s_red[1][w]; }
+        a.partials[2 * cta] = l; a.partials[2 * cta + 1] = c;
+        __threadfence();
+        unsigned done = atomicAdd(&a.stats[2], 1u);
+        s_last = done == n_ctas - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double l = 0.0, c = 0.0;
+        for (unsigned i = tid; i < n_ctas; i += LOSS_NT) {           // fixed order -> deterministic
+            l += __ldcg(&a.partials[2 * i]); c += __ldcg(&a.partials[2 * i + 1]);
+        }
+        l = warp_sum(l); c = warp_sum(c);
+        if (lane == 0) { s_red[0][warp] = l; s_red[1][warp] = c; }
+        __syncthreads();
+        if (tid == 0) {
+            l = 0.0; c = 0.0;
+            for (int w = 0; w < LOSS_NT / 32; ++w) { l += s_red[0][w]; c += s_red[1][w]; }
+            a.losses[0] = __fdiv_rn((float)l, (float)n_total);        // multibox_loss.py:117-119
+            a.losses[1] = __fdiv_rn((float)c, (float)n_total);
+            a.stats[2] = 0;
+        }
+    }
+}
+
+int pick_cluster_loss(int B, int P) {
+    int s = 1;
+    while (s < 8 && B * s < 296 && P / (s * 2) >= 512) s *= 2;
+    return s;
+}
+
+static size_t loss_smem_bytes(int g_max, int slice) {
+    return (size_t)((g_max + 3) & ~3) * 5 * 4 + (size_t)slice * 4 + 16;
+}
+
+template <bool C2, bool CL, bool GR>
+static int launch_loss(LossArgs &a, int S, int g_max, cudaStream_t stream) {
+    auto kern = loss_kernel<C2, CL, GR>;
+    size_t smem = loss_smem_bytes(g_max, a.slice);
+    if (smem > 48 * 1024)
+        GSSD_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(S, a.B, 1);
+    cfg.blockDim = dim3(LOSS_NT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    GSSD_RETURN_IF_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    GSSD_AFTER_LAUNCH();
+    return GSSD_OK;
+}
+
+// ---- backward helper: in-place scaling by the upstream gradients, free when they are 1 ------------
+__global__ void __launch_bounds__(256) scale_grads_kernel(float4 *gl, size_t n4_loc, float4 *gc, size_t n4_conf,
+                                                          float *gc_tail, int n_tail,
+                                                          const float *g_loc, const float *g_conf) {
+    const float sl = g_loc ? *g_loc : 1.f, sc = g_conf ? *g_conf : 1.f;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sl != 1.f)
+        for (size_t i = t0; i < n4_loc; i += stride) { float4 v = gl[i]; v.x *= sl; v.y *= sl; v.z *= sl; v.w *= sl; gl[i] = v; }
+    if (sc != 1.f) {
+        for (size_t i = t0; i < n4_conf; i += stride) { float4 v = gc[i]; v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; gc[i] = v; }
+        if (t0 < (size_t)n_tail) gc_tail[t0] *= sc;
+    }
+}
+
+}  // namespace gssd
+
+using namespace gssd;
+
+extern "C" size_t gssd_stats_bytes(int B) { return sizeof(gssd_loss_stats) + sizeof(int32_t) * (size_t)(B > 0 ? B : 0); }
+
+extern "C" int gssd_mbox_loss(const float *loc, const float *conf, const float *priors, int B, int P, int C,
+                              const float *gt, const int32_t *gt_off, int sum_G, int g_max,
+                              const uint16_t *tags, void *stats_buf,
+                              const gssd_loss_stats *global_stats, int n_global_stats,
+                              int negpos_ratio, float var0, float var1,
+                              float *losses, float *grad_loc, float *grad_conf,
+                              uint8_t *pos_mask, uint8_t *neg_mask,
+                              void *ws, size_t ws_bytes, void *stream) {
+    if (!loc || !conf || !priors || !gt || !gt_off || !tags || !stats_buf || !losses || !ws) return GSSD_ERR_ARG;
+    if (B <= 0 || P <= 0 || sum_G <= 0 || g_max <= 0 || negpos_ratio < 0) return GSSD_ERR_ARG;
+    if (C < 2 || C > GSSD_MAX_CLASSES) return GSSD_ERR_ARG;
+    if ((grad_loc == nullptr) != (grad_conf == nullptr)) return GSSD_ERR_ARG;
+    if (g_max > GSSD_MAX_GT_PER_IMAGE || P > GSSD_MAX_PRIORS) return GSSD_ERR_LIMIT;
+    if (global_stats && n_global_stats <= 0) return GSSD_ERR_ARG;
+    const int S = pick_cluster_loss(B, P);
+    if (ws_bytes < gssd_workspace_bytes(GSSD_WS_LOSS, B, P, C, sum_G, 0)) return GSSD_ERR_WS;
+    LossArgs a = {};
+    a.loc = reinterpret_cast<const float4 *>(loc); a.conf = conf; a.priors = reinterpret_cast<const float4 *>(priors);
+    a.B = B; a.P = P; a.C = C; a.gt = gt; a.gt_off = gt_off; a.tags = tags;
+    a.stats = reinterpret_cast<uint32_t *>(stats_buf);
+    a.gstats = reinterpret_cast<const uint32_t *>(global_stats); a.n_gstats = n_global_stats;
+    a.ratio = negpos_ratio; a.var0 = var0; a.var1 = var1;
+    a.losses = losses; a.grad_loc = reinterpret_cast<float4 *>(grad_loc); a.grad_conf = grad_conf;
+    a.pos_mask = pos_mask; a.neg_mask = neg_mask;
+    a.partials = reinterpret_cast<double *>(ws);
+    a.slice = ceil_div(P, S);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool gr = grad_loc != nullptr;
+    const bool c2 = C == 2;
+#define GSSD_LOSS_CASE(C2_, CL_, GR_) if (c2 == C2_ && (S > 1) == CL_ && gr == GR_) return launch_loss<C2_, CL_, GR_>(a, S, g_max, st);
+    GSSD_LOSS_CASE(true, true, true) GSSD_LOSS_CASE(true, true, false)
+    GSSD_LOSS_CASE(true, false, true) GSSD_LOSS_CASE(true, false, false)
+    GSSD_LOSS_CASE(false, true, true) GSSD_LOSS_CASE(false, true, false)
+    GSSD_LOSS_CASE(false, false, true) GSSD_LOSS_CASE(false, false, false)
+#undef GSSD_LOSS_CASE
+    return GSSD_ERR_ARG;
+}
+
+extern "C" int gssd_mbox_scale_grads(float *grad_loc, size_t n_loc, float *grad_conf, size_t n_conf,
+                                     const float *g_loc, const float *g_conf, void *stream) {
+    if (!grad_loc || !grad_conf) return GSSD_ERR_ARG;
+    if (n_loc % 4) return GSSD_ERR_ARG;
+    size_t n4c = n_conf / 4; int tail = (int)(n_conf % 4);
+    size_t work = (n_loc / 4 > n4c ? n_loc / 4 : n4c);
+    int blocks = (int)((work + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    scale_grads_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float4 *>(grad_loc), n_loc / 4, reinterpret_cast<float4 *>(grad_conf), n4c,
+        grad_conf + n4c * 4, tail, g_loc, g_conf);
+    GSSD_AFTER_LAUNCH();
+    return GSSD_OK;
+}

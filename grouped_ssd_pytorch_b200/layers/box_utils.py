@@ -1,0 +1,169 @@
+"""box_utils — same functions and signatures as layers/box_utils.py of the reference, computed by
+libgssd_b200.so.  Tensors may live on the CPU or on a CUDA device; results come back on the device of
+the first argument.  There is no CPU implementation: a CUDA device is required."""
+import torch
+
+from .. import _lib
+
+
+def _run(first, fn):
+    dev = _lib.device_of(first)
+    with torch.cuda.device(dev):
+        out = fn(dev)
+    return out if (not isinstance(first, torch.Tensor)) or first.is_cuda else out.cpu()
+
+
+def point_form(boxes):
+    """(cx, cy, w, h) -> (xmin, ymin, xmax, ymax)   [box_utils.py:4-13]"""
+    lib = _lib.require_cuda()
+
+    def go(dev):
+        b = _lib.f32(boxes, dev)
+        out = torch.empty_like(b)
+        _lib.check(lib.gssd_point_form(b.data_ptr(), b.size(0), out.data_ptr(), _lib.stream()))
+        return out
+    return _run(boxes, go)
+
+
+def center_size(boxes):
+    """(xmin, ymin, xmax, ymax) -> (cx, cy, w, h)   [box_utils.py:16-25, documented intent]"""
+    lib = _lib.require_cuda()
+
+    def go(dev):
+        b = _lib.f32(boxes, dev)
+        out = torch.empty_like(b)
+        _lib.check(lib.gssd_center_size(b.data_ptr(), b.size(0), out.data_ptr(), _lib.stream()))
+        return out
+    return _run(boxes, go)
+
+
+def _pair(name, box_a, box_b):
+    lib = _lib.require_cuda()
+
+    def go(dev):
+        a, b = _lib.f32(box_a, dev), _lib.f32(box_b, dev)
+        out = torch.empty((a.size(0), b.size(0)), dtype=torch.float32, device=dev)
+        _lib.check(getattr(lib, name)(a.data_ptr(), a.size(0), b.data_ptr(), b.size(0), out.data_ptr(), _lib.stream()))
+        return out
+    return _run(box_a, go)
+
+
+def intersect(box_a, box_b):
+    """[A,4], [B,4] point form -> intersection areas [A,B]   [box_utils.py:28-46]"""
+    return _pair("gssd_intersect", box_a, box_b)
+
+
+def jaccard(box_a, box_b):
+    """IoU matrix [A,B]; union = area_a + area_b - inter   [box_utils.py:49-67]"""
+    return _pair("gssd_jaccard", box_a, box_b)
+
+
+def pack_targets(truths_list, labels_list, dev):
+    """per-image (truths[G,4], labels[G]) -> gt[sum_G,5] on `dev`, gt_off[B+1] int32 on `dev`,
+    sum_G, g_max.  Raises IndexError for an image without boxes (reference: box_utils.py:94)."""
+    offs = [0]
+    rows = []
+    for t, l in zip(truths_list, labels_list):
+        g = int(t.size(0)) if t.dim() > 0 else 0
+        if g == 0:
+            raise IndexError("match: an image has no ground-truth box")
+        offs.append(offs[-1] + g)
+        rows.append(torch.cat([t.detach().reshape(g, 4).float(), l.detach().reshape(g, 1).float()], 1))
+    gt = (rows[0] if len(rows) == 1 else torch.cat(rows, 0)).to(dev).contiguous()
+    gt_off = torch.tensor(offs, dtype=torch.int32).to(dev)
+    g_max = max(b - a for a, b in zip(offs[:-1], offs[1:]))
+    return gt, gt_off, offs[-1], g_max
+
+
+def match(threshold, truths, priors, variances, labels, loc_t, conf_t, idx):
+    """Match priors with ground truth, encode, and write loc_t[idx], conf_t[idx] in place
+    [box_utils.py:70-111]."""
+    lib = _lib.require_cuda()
+    dev = _lib.device_of(truths, priors, loc_t)
+    with torch.cuda.device(dev):
+        pri = _lib.f32(priors, dev)
+        P = pri.size(0)
+        gt, gt_off, sum_g, g_max = pack_targets([truths], [labels], dev)
+        direct = loc_t.is_cuda and conf_t.is_cuda and loc_t.dtype == torch.float32 and conf_t.dtype == torch.int64 \
+            and loc_t[idx].is_contiguous() and conf_t[idx].is_contiguous()
+        lo = loc_t[idx] if direct else torch.empty((P, 4), dtype=torch.float32, device=dev)
+        co = conf_t[idx] if direct else torch.empty((P,), dtype=torch.int64, device=dev)
+        _lib.check(lib.gssd_match(pri.data_ptr(), P, gt.data_ptr(), gt_off.data_ptr(), 1, sum_g, g_max,
+                                  float(threshold), float(variances[0]), float(variances[1]),
+                                  lo.data_ptr(), co.data_ptr(), None, None, 0, _lib.stream()), "match")
+        if not direct:
+            loc_t[idx] = lo.to(loc_t.device)
+            conf_t[idx] = co.to(conf_t.device)
+
+
+def match_batch(threshold, targets, priors, variances, return_idx=False):
+    """Batched form of the loop at multibox_loss.py:67-72: targets = list of [n_i,5] tensors.
+    -> loc_t[B,P,4] float32, conf_t[B,P] int64 (, best_truth_idx[B,P] int32) on the GPU."""
+    lib = _lib.require_cuda()
+    dev = _lib.device_of(priors, *targets)
+    with torch.cuda.device(dev):
+        pri = _lib.f32(priors, dev)
+        P, B = pri.size(0), len(targets)
+        gt, gt_off, sum_g, g_max = pack_targets([t[:, :-1] for t in targets], [t[:, -1] for t in targets], dev)
+        loc_t = torch.empty((B, P, 4), dtype=torch.float32, device=dev)
+        conf_t = torch.empty((B, P), dtype=torch.int64, device=dev)
+        bti = torch.empty((B, P), dtype=torch.int32, device=dev) if return_idx else None
+        _lib.check(lib.gssd_match(pri.data_ptr(), P, gt.data_ptr(), gt_off.data_ptr(), B, sum_g, g_max,
+                                  float(threshold), float(variances[0]), float(variances[1]),
+                                  loc_t.data_ptr(), conf_t.data_ptr(), _lib.ptr(bti), None, 0, _lib.stream()), "match")
+    return (loc_t, conf_t, bti) if return_idx else (loc_t, conf_t)
+
+
+def _codec(name, x, priors, variances):
+    lib = _lib.require_cuda()
+
+    def go(dev):
+        a, p = _lib.f32(x, dev), _lib.f32(priors, dev)
+        out = torch.empty_like(a)
+        _lib.check(getattr(lib, name)(a.data_ptr(), p.data_ptr(), a.size(0), float(variances[0]),
+                                      float(variances[1]), out.data_ptr(), _lib.stream()))
+        return out
+    return _run(x, go)
+
+
+def encode(matched, priors, variances):
+    """point-form matched boxes + center-form priors -> regression targets   [box_utils.py:114-135]"""
+    return _codec("gssd_encode", matched, priors, variances)
+
+
+def decode(loc, priors, variances):
+    """loc predictions + center-form priors -> point-form boxes   [box_utils.py:139-157]"""
+    return _codec("gssd_decode", loc, priors, variances)
+
+
+def log_sum_exp(x):
+    """log(sum(exp(x - max(x)), 1, keepdim=True)) + max(x), max over the WHOLE tensor
+    [box_utils.py:160-168]"""
+    lib = _lib.require_cuda()
+
+    def go(dev):
+        a = _lib.f32(x, dev)
+        out = torch.empty((a.size(0), 1), dtype=torch.float32, device=dev)
+        ws = torch.empty(4, dtype=torch.int32, device=dev)
+        _lib.check(lib.gssd_log_sum_exp(a.data_ptr(), a.size(0), a.size(1), out.data_ptr(), ws.data_ptr(), 16,
+                                        _lib.stream()))
+        return out
+    return _run(x, go)
+
+
+def nms(boxes, scores, overlap=0.5, top_k=200):
+    """Greedy NMS over the top_k highest scores -> (keep LongTensor[n] zero padded, count)
+    [box_utils.py:174-238].  Like the reference it returns the bare `keep` for an empty input."""
+    lib = _lib.require_cuda()
+    n = int(scores.size(0))
+    if boxes.numel() == 0:                              # box_utils.py:186-188
+        return scores.new_zeros((n,), dtype=torch.long)
+    dev = _lib.device_of(boxes, scores)
+    with torch.cuda.device(dev):
+        b, s = _lib.f32(boxes, dev), _lib.f32(scores, dev)
+        keep = torch.empty((n,), dtype=torch.int64, device=dev)
+        count = torch.empty((1,), dtype=torch.int32, device=dev)
+        _lib.check(lib.gssd_nms(b.data_ptr(), s.data_ptr(), n, float(overlap), int(top_k), keep.data_ptr(),
+                                count.data_ptr(), None, 0, _lib.stream()), "nms")
+        cnt = int(count.item())                         # the reference returns a Python int (box_utils.py:238)
+    return (keep if scores.is_cuda else keep.cpu()), cnt

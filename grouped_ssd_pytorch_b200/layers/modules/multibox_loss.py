@@ -1,0 +1,147 @@
+"""MultiBoxLoss — same constructor and forward as layers/modules/multibox_loss.py:8-120 of the
+reference; the whole forward (matching, encoding, smooth-L1, hard-negative mining, cross-entropy,
+normalisation) and its backward run in two kernel launches of libgssd_b200.so."""
+import torch
+import torch.nn as nn
+
+from ... import _lib
+from ...config import v2 as cfg
+from ..box_utils import pack_targets
+
+
+def _dist_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_world_size()
+    return None, 1
+
+
+class _MultiBoxLossFn(torch.autograd.Function):
+    """(loc, conf) -> (loss_l, loss_c) with d(loss_l)/d(loc) and d(loss_c)/d(conf) produced by the
+    forward kernel; backward only rescales them by the upstream gradients (a no-op kernel when both
+    are 1, i.e. `(loss_l + loss_c).backward()`, train_lesion_multiphase_v2.py:247-248)."""
+
+    @staticmethod
+    def forward(ctx, loc, conf, priors, gt, gt_off, sum_g, g_max, threshold, negpos_ratio, variance, masks, group):
+        lib = _lib.require_cuda()
+        dev = loc.device
+        B, P, C = conf.shape
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        st = _lib.stream()
+        tags = torch.empty((B, P), dtype=torch.int16, device=dev)
+        stats = torch.empty((_lib.STATS_HEADER_BYTES + 4 * B,), dtype=torch.uint8, device=dev)
+        _lib.check(lib.gssd_mbox_match(priors.data_ptr(), P, conf.data_ptr(), C, gt.data_ptr(), gt_off.data_ptr(),
+                                       B, sum_g, g_max, float(threshold), tags.data_ptr(), stats.data_ptr(), st),
+                   "gssd_mbox_match")
+        # DataParallel semantics of the reference: x_max and N are over the GLOBAL batch
+        # (train_lesion_multiphase_v2.py:242-246 -> multibox_loss.py:117, box_utils.py:167).
+        gstats, n_g = None, 0
+        dist, world = _dist_world()
+        if world > 1 and group is not False:
+            gstats = torch.empty((world * _lib.STATS_HEADER_BYTES,), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(gstats, stats[:_lib.STATS_HEADER_BYTES], group=group or None)
+            n_g = world
+        losses = torch.empty((2,), dtype=torch.float32, device=dev)
+        grad_loc = torch.empty_like(loc) if need_grad else None
+        grad_conf = torch.empty_like(conf) if need_grad else None
+        pos = torch.empty((B, P), dtype=torch.uint8, device=dev) if masks else None
+        neg = torch.empty((B, P), dtype=torch.uint8, device=dev) if masks else None
+        ws_bytes = lib.gssd_workspace_bytes(_lib.WS_LOSS, B, P, C, sum_g, 0)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        _lib.check(lib.gssd_mbox_loss(loc.data_ptr(), conf.data_ptr(), priors.data_ptr(), B, P, C,
+                                      gt.data_ptr(), gt_off.data_ptr(), sum_g, g_max, tags.data_ptr(), stats.data_ptr(),
+                                      _lib.ptr(gstats), n_g, int(negpos_ratio), float(variance[0]), float(variance[1]),
+                                      losses.data_ptr(), _lib.ptr(grad_loc), _lib.ptr(grad_conf),
+                                      _lib.ptr(pos), _lib.ptr(neg), ws.data_ptr(), ws_bytes, st), "gssd_mbox_loss")
+        ctx.grads = (grad_loc, grad_conf)
+        num_pos = stats[_lib.STATS_HEADER_BYTES:].view(torch.int32)
+        aux = [t for t in (pos, neg, num_pos) if t is not None]
+        ctx.mark_non_differentiable(*aux)
+        return losses[0], losses[1], pos, neg, num_pos
+
+    @staticmethod
+    def backward(ctx, g_l, g_c, *_unused):
+        grad_loc, grad_conf = ctx.grads
+        if grad_loc is None:
+            return (None,) * 12
+        lib = _lib.load()
+        with torch.cuda.device(grad_loc.device):
+            g_l = g_l.to(device=grad_loc.device, dtype=torch.float32).contiguous()
+            g_c = g_c.to(device=grad_loc.device, dtype=torch.float32).contiguous()
+            _lib.check(lib.gssd_mbox_scale_grads(grad_loc.data_ptr(), grad_loc.numel(), grad_conf.data_ptr(),
+                                                 grad_conf.numel(), g_l.data_ptr(), g_c.data_ptr(), _lib.stream()),
+                       "gssd_mbox_scale_grads")
+        return (grad_loc, grad_conf) + (None,) * 10
+
+
+class MultiBoxLoss(nn.Module):
+    """SSD weighted loss (multibox_loss.py:8-29): L = (Lconf + Lloc) / N with
+    1) prior <-> ground-truth matching at `overlap_thresh`, 2) variance-encoded offsets,
+    3) hard-negative mining at `neg_pos`:1.
+
+    Constructor arguments are the reference's (multibox_loss.py:31-44); only `num_classes`,
+    `overlap_thresh` and `neg_pos` influence the result there, and the same holds here.
+
+    Extra attributes (not in the reference):
+      process_group : None = default group when torch.distributed is initialised with world_size > 1
+                      (x_max and N then span the global batch, as under the reference's DataParallel);
+                      False = keep both statistics local to this rank.
+      keep_masks    : also produce the positive / hard-negative masks (`last_masks`) for inspection.
+    With world_size > 1 the returned losses hold this rank's numerators over the global N: their sum
+    over ranks is the reference's loss."""
+
+    def __init__(self, num_classes, overlap_thresh, prior_for_matching,
+                 bkg_label, neg_mining, neg_pos, neg_overlap, encode_target,
+                 use_gpu=True):
+        super(MultiBoxLoss, self).__init__()
+        self.use_gpu = use_gpu
+        self.num_classes = num_classes
+        self.threshold = overlap_thresh
+        self.background_label = bkg_label
+        self.encode_target = encode_target
+        self.use_prior_for_matching = prior_for_matching
+        self.do_neg_mining = neg_mining
+        self.negpos_ratio = neg_pos
+        self.neg_overlap = neg_overlap
+        self.variance = cfg['variance']          # multibox_loss.py:44
+        self.process_group = None
+        self.keep_masks = False
+        self.last_masks = None
+        self._prior_cache = {}
+
+    def _device_priors(self, priors, dev):
+        if priors.is_cuda and priors.dtype == torch.float32 and priors.is_contiguous() and priors.device == dev:
+            return priors.detach()
+        key = (priors.data_ptr(), tuple(priors.shape), priors._version, str(dev))
+        hit = self._prior_cache.get(key)
+        if hit is None:
+            self._prior_cache.clear()
+            hit = _lib.f32(priors, dev)
+            self._prior_cache[key] = hit
+        return hit
+
+    def forward(self, predictions, targets):
+        """predictions = (loc[B,P,4], conf[B,P,C], priors[P,4]); targets = list of [n_i,5] tensors
+        (xmin,ymin,xmax,ymax,label), CPU or CUDA (multibox_loss.py:46-57) -> (loss_l, loss_c)."""
+        _lib.require_cuda()
+        loc_data, conf_data, priors = predictions
+        num = loc_data.size(0)
+        priors = priors[:loc_data.size(1), :]                  # multibox_loss.py:60
+        dev = _lib.device_of(loc_data, conf_data)
+        out_dev = loc_data.device
+        with torch.cuda.device(dev):
+            loc = loc_data.to(device=dev, dtype=torch.float32).contiguous()
+            conf = conf_data.to(device=dev, dtype=torch.float32).contiguous()
+            if conf.dim() == 2:
+                conf = conf.view(num, -1, self.num_classes)
+            pri = self._device_priors(priors, dev)
+            tl = [targets[i] for i in range(num)]
+            gt, gt_off, sum_g, g_max = pack_targets([t[:, :-1] for t in tl], [t[:, -1] for t in tl], dev)
+            loss_l, loss_c, pos, neg, num_pos = _MultiBoxLossFn.apply(
+                loc, conf, pri, gt, gt_off, sum_g, g_max, self.threshold, self.negpos_ratio, self.variance,
+                self.keep_masks, self.process_group)
+            if self.keep_masks:
+                self.last_masks = dict(pos=pos, neg=neg, num_pos=num_pos)
+        if out_dev != dev:
+            loss_l, loss_c = loss_l.to(out_dev), loss_c.to(out_dev)
+        return loss_l, loss_c

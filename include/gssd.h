@@ -33,6 +33,12 @@ extern "C" {
 
 #define GSSD_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define GSSD_API __attribute__((visibility("default")))
+#else
+#define GSSD_API
+#endif
+
 #define GSSD_OK          0
 #define GSSD_ERR_ARG    -1   /* null pointer / non-positive size / bad enum */
 #define GSSD_ERR_LIMIT  -2   /* size beyond what the kernels support (see GSSD_MAX_*) */
@@ -47,10 +53,10 @@ extern "C" {
 #define GSSD_MAX_FEATURE_MAPS     8
 #define GSSD_MAX_ASPECT_RATIOS    8
 
-int         gssd_abi_version(void);
-const char *gssd_error_string(int code);
+GSSD_API int         gssd_abi_version(void);
+GSSD_API const char *gssd_error_string(int code);
 /* number of kernels launched by this library since load (bench.py's gpu_launches claim) */
-uint64_t    gssd_launch_count(void);
+GSSD_API uint64_t    gssd_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * PriorBox — replaces PriorBox.__init__/forward, layers/functions/prior_box.py:14-172
@@ -76,30 +82,30 @@ typedef struct gssd_prior_cfg {
 } gssd_prior_cfg;
 
 /* host-only: number of boxes P the config generates, or a negative GSSD_ERR_* */
-int gssd_priorbox_count(const gssd_prior_cfg *cfg_host);
+GSSD_API int gssd_priorbox_count(const gssd_prior_cfg *cfg_host);
 /* out[P,4] float32.  fp64 arithmetic in the reference's order, one rounding to fp32, then clamp. */
-int gssd_priorbox(const gssd_prior_cfg *cfg_host, float *out, void *stream);
+GSSD_API int gssd_priorbox(const gssd_prior_cfg *cfg_host, float *out, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * box_utils — replaces layers/box_utils.py
  * ---------------------------------------------------------------------------------------- */
 /* point_form, box_utils.py:4-13 : (cx,cy,w,h) -> (xmin,ymin,xmax,ymax), [n,4] -> [n,4] */
-int gssd_point_form(const float *boxes, int n, float *out, void *stream);
+GSSD_API int gssd_point_form(const float *boxes, int n, float *out, void *stream);
 /* center_size, box_utils.py:16-25 (documented intent; the reference body is malformed) */
-int gssd_center_size(const float *boxes, int n, float *out, void *stream);
+GSSD_API int gssd_center_size(const float *boxes, int n, float *out, void *stream);
 /* intersect, box_utils.py:28-46 : a[A,4], b[Bn,4] point form -> out[A,Bn] */
-int gssd_intersect(const float *a, int A, const float *b, int Bn, float *out, void *stream);
+GSSD_API int gssd_intersect(const float *a, int A, const float *b, int Bn, float *out, void *stream);
 /* jaccard, box_utils.py:49-67 : IoU matrix out[A,Bn]; union = (area_a + area_b) - inter */
-int gssd_jaccard(const float *a, int A, const float *b, int Bn, float *out, void *stream);
+GSSD_API int gssd_jaccard(const float *a, int A, const float *b, int Bn, float *out, void *stream);
 /* encode, box_utils.py:114-135 : matched[n,4] point form, priors[n,4] center form -> out[n,4] */
-int gssd_encode(const float *matched, const float *priors, int n, float var0, float var1,
+GSSD_API int gssd_encode(const float *matched, const float *priors, int n, float var0, float var1,
                 float *out, void *stream);
 /* decode, box_utils.py:139-157 : loc[n,4], priors[n,4] -> out[n,4] point form (not clipped) */
-int gssd_decode(const float *loc, const float *priors, int n, float var0, float var1,
+GSSD_API int gssd_decode(const float *loc, const float *priors, int n, float var0, float var1,
                 float *out, void *stream);
 /* log_sum_exp, box_utils.py:160-168 : x[rows,C] -> out[rows]; subtracts the max of the WHOLE
  * tensor.  ws: gssd_workspace_bytes(GSSD_WS_LSE, ...) */
-int gssd_log_sum_exp(const float *x, int rows, int C, float *out, void *ws, size_t ws_bytes,
+GSSD_API int gssd_log_sum_exp(const float *x, int rows, int C, float *out, void *ws, size_t ws_bytes,
                      void *stream);
 
 /* match, box_utils.py:70-111, batched over B images (the loop at multibox_loss.py:67-72).
@@ -107,7 +113,7 @@ int gssd_log_sum_exp(const float *x, int rows, int C, float *out, void *ws, size
  *   loc_t[B,P,4] float32 and conf_t[B,P] int64 are written for every prior (box_utils.py:109-111);
  *   best_truth_idx[B,P] int32 (optional, may be NULL) = final matched GT row within the image.
  * Ties: argmax -> lowest index; shared best prior -> highest GT row wins (box_utils.py:104-105). */
-int gssd_match(const float *priors, int P, const float *gt, const int32_t *gt_off, int B,
+GSSD_API int gssd_match(const float *priors, int P, const float *gt, const int32_t *gt_off, int B,
                int sum_G, int g_max, float threshold, float var0, float var1,
                float *loc_t, int64_t *conf_t, int32_t *best_truth_idx,
                void *ws, size_t ws_bytes, void *stream);
@@ -116,7 +122,7 @@ int gssd_match(const float *priors, int P, const float *gt, const int32_t *gt_of
  *   keep[n] int64 zero-padded, count[1] int32 (device).  Candidates are the top_k scores BEFORE
  *   suppression; union = (area_j - inter) + area_i; kept iff IoU <= overlap.
  *   Equal scores: higher index first (stable ascending sort read from the end). */
-int gssd_nms(const float *boxes, const float *scores, int n, float overlap, int top_k,
+GSSD_API int gssd_nms(const float *boxes, const float *scores, int n, float overlap, int top_k,
              int64_t *keep, int32_t *count, void *ws, size_t ws_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -125,29 +131,37 @@ int gssd_nms(const float *boxes, const float *scores, int n, float overlap, int 
  * two batch-global scalars between them (stats[0] = max of conf as float bits, MAX;
  * stats[1] = number of positives N as int32, SUM).
  * ---------------------------------------------------------------------------------------- */
-typedef struct gssd_loss_stats {     /* device-resident, 16 bytes */
-    float   conf_max;                /* x_max of log_sum_exp (box_utils.py:167), whole local batch */
-    int32_t num_pos_total;           /* N (multibox_loss.py:117) */
-    int32_t reserved[2];
+typedef struct gssd_loss_stats {     /* device-resident header, 16 bytes */
+    uint32_t conf_max_ord;           /* x_max of log_sum_exp (box_utils.py:167) over the local batch, as an
+                                        order-preserving uint32 (0 = "no value"); combine with MAX */
+    int32_t  num_pos_total;          /* local part of N (multibox_loss.py:117); combine with SUM */
+    uint32_t done_counter;           /* internal (last-CTA reduction of stage 2) */
+    uint32_t reserved;
 } gssd_loss_stats;
+/* stats_buf = [gssd_loss_stats header][int32 num_pos[B]] : gssd_stats_bytes(B) bytes */
+GSSD_API size_t gssd_stats_bytes(int B);
 
-/* Stage 1: matching (box_utils.py:70-108) + batch max of conf.
+/* Stage 1: matching (box_utils.py:70-108) + batch max of conf (conf may be NULL: header max stays 0).
  *   tags[B,P] uint16 : bit15 = positive, bits0-14 = matched GT row within the image
- *   num_pos[B] int32, stats (zero-initialised by this call). */
-int gssd_mbox_match(const float *priors, int P, const float *conf, int C,
+ *   stats_buf is zeroed and filled by this call. */
+GSSD_API int gssd_mbox_match(const float *priors, int P, const float *conf, int C,
                     const float *gt, const int32_t *gt_off, int B, int sum_G, int g_max,
-                    float threshold, uint16_t *tags, int32_t *num_pos, gssd_loss_stats *stats,
-                    void *stream);
+                    float threshold, uint16_t *tags, void *stats_buf, void *stream);
 
 /* Stage 2: encode + smooth-L1 (multibox_loss.py:80-88), mining key with the global-max LSE
  * (91-101), hard-negative selection of min(negpos_ratio*num_pos, P-1) keys per image (102-106;
  * descending key, ties -> lower prior index), cross-entropy over pos|neg (108-113), division by N
  * (117-119) and the gradients of both losses.
- *   losses[2] float32 = (loss_l/N, loss_c/N);  grad_loc[B,P,4], grad_conf[B,P,C] = d(loss_l)/d(loc),
- *   d(loss_c)/d(conf) (NULL, NULL for forward only); pos_mask/neg_mask[B,P] uint8 optional. */
-int gssd_mbox_loss(const float *loc, const float *conf, const float *priors, int B, int P, int C,
+ *   stats_buf: as filled by stage 1 on this device.  global_stats[n_global_stats]: the headers of
+ *   every rank of a data-parallel job (all-gathered by the host; MAX / SUM are taken in-kernel), or
+ *   NULL,0 to use the local header alone.
+ *   losses[2] float32 = (loss_l/N, loss_c/N) with this device's images in the numerators;
+ *   grad_loc[B,P,4], grad_conf[B,P,C] = d(loss_l)/d(loc), d(loss_c)/d(conf) (NULL, NULL for forward
+ *   only); pos_mask/neg_mask[B,P] uint8 optional. */
+GSSD_API int gssd_mbox_loss(const float *loc, const float *conf, const float *priors, int B, int P, int C,
                    const float *gt, const int32_t *gt_off, int sum_G, int g_max,
-                   const uint16_t *tags, const int32_t *num_pos, const gssd_loss_stats *stats,
+                   const uint16_t *tags, void *stats_buf,
+                   const gssd_loss_stats *global_stats, int n_global_stats,
                    int negpos_ratio, float var0, float var1,
                    float *losses, float *grad_loc, float *grad_conf,
                    uint8_t *pos_mask, uint8_t *neg_mask,
@@ -156,7 +170,7 @@ int gssd_mbox_loss(const float *loc, const float *conf, const float *priors, int
 /* Backward helper: grad_loc *= g[0], grad_conf *= g[1] in place (g = upstream gradients of the two
  * scalar losses, device).  Touches no memory when g == (1,1), the `(loss_l+loss_c).backward()` case
  * of train_lesion_multiphase_v2.py:247-248. */
-int gssd_mbox_scale_grads(float *grad_loc, size_t n_loc, float *grad_conf, size_t n_conf,
+GSSD_API int gssd_mbox_scale_grads(float *grad_loc, size_t n_loc, float *grad_conf, size_t n_conf,
                           const float *g_loc, const float *g_conf, void *stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -166,7 +180,7 @@ int gssd_mbox_scale_grads(float *grad_loc, size_t n_loc, float *grad_conf, size_
  *   out[B,C,top_k,5] rows (score,xmin,ymin,xmax,ymax) in descending score, zero-padded; class 0
  *   slab is all zero; count[B,C] int32 and keep_idx[B,C,top_k] int32 (prior index, -1 padded) are
  *   optional (may be NULL). */
-int gssd_detect(const float *loc, const float *conf, const float *priors, int B, int P, int C,
+GSSD_API int gssd_detect(const float *loc, const float *conf, const float *priors, int B, int P, int C,
                 int top_k, float conf_thresh, float nms_thresh, float var0, float var1,
                 float *out, int32_t *count, int32_t *keep_idx, void *stream);
 
@@ -174,18 +188,19 @@ int gssd_detect(const float *loc, const float *conf, const float *priors, int B,
  * L2Norm — replaces L2Norm.forward, layers/modules/l2norm.py:19-23, and its backward.
  *   x[B,Cn,HW] (NCHW), weight[Cn]; y = weight[c] * x / (sqrt(sum_c x^2) + eps)
  * ---------------------------------------------------------------------------------------- */
-int gssd_l2norm_fwd(const float *x, const float *weight, int B, int Cn, int HW, float eps,
+GSSD_API int gssd_l2norm_fwd(const float *x, const float *weight, int B, int Cn, int HW, float eps,
                     float *y, float *norm /* [B,HW], saved for backward, may be NULL */, void *stream);
-int gssd_l2norm_bwd(const float *x, const float *weight, const float *norm, const float *gy,
-                    int B, int Cn, int HW, float eps, float *gx,
-                    float *gw_partial /* [n_partial,Cn] */, int n_partial, void *stream);
-int gssd_l2norm_bwd_partials(int B, int Cn, int HW);
+/* gx[B,Cn,HW], gw[Cn]; ws: gssd_l2norm_bwd_ws_bytes() bytes of scratch (per-CTA partial sums of gw) */
+GSSD_API int gssd_l2norm_bwd(const float *x, const float *weight, const float *norm, const float *gy,
+                    int B, int Cn, int HW, float eps, float *gx, float *gw,
+                    void *ws, size_t ws_bytes, void *stream);
+GSSD_API size_t gssd_l2norm_bwd_ws_bytes(int B, int Cn, int HW);
 
 /* ------------------------------------------------------------------------------------------
  * workspace sizing (host-only)
  * ---------------------------------------------------------------------------------------- */
 enum { GSSD_WS_LSE = 0, GSSD_WS_MATCH = 1, GSSD_WS_LOSS = 2, GSSD_WS_NMS = 3 };
-size_t gssd_workspace_bytes(int kind, int B, int P, int C, int sum_G, int top_k);
+GSSD_API size_t gssd_workspace_bytes(int kind, int B, int P, int C, int sum_G, int top_k);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,164 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol
+include/gssd.h declares; the host layer mirrors the reference's module tree and error behaviour and
+refuses to run without a CUDA device (no CPU fallback).  No compute call is made here."""
+import ctypes
+import inspect
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import cases
+import grouped_ssd_pytorch_b200 as pkg
+from grouped_ssd_pytorch_b200 import _lib, build, config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "gssd.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"GSSD_API[^;(]*?\b(gssd_\w+)\s*\(", text)))
+
+
+def test_header_declares_the_hot_path():
+    syms = declared_symbols()
+    for must in ("gssd_priorbox", "gssd_jaccard", "gssd_match", "gssd_encode", "gssd_decode", "gssd_nms",
+                 "gssd_mbox_match", "gssd_mbox_loss", "gssd_detect", "gssd_l2norm_fwd", "gssd_log_sum_exp"):
+        assert must in syms
+    assert len(syms) >= 20
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    for s in declared_symbols():
+        assert hasattr(lib, s), "libgssd_b200.so does not export " + s
+    assert lib.gssd_abi_version() == 1
+    out = subprocess.check_output(["nm", "-D", "--defined-only", path], text=True)
+    exported = set(re.findall(r" T (\w+)", out))
+    extra = {e for e in exported if not e.startswith("gssd_")}
+    assert not extra, "unexpected exports: %s" % sorted(extra)[:5]
+
+
+def test_binding_table_matches_header():
+    assert sorted(_lib._SIGS) == declared_symbols()
+    lib = _lib.load()
+    assert lib.gssd_error_string(-4).decode().startswith("value error")
+    assert lib.gssd_stats_bytes(32) == 16 + 4 * 32
+    assert lib.gssd_workspace_bytes(_lib.WS_LOSS, 32, 8732, 2, 100, 0) >= 32 * 8 * 16
+
+
+def test_sm100a_code_is_in_the_library():
+    out = subprocess.run(["cuobjdump", "-lelf", build.LIB], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+
+
+def test_priorbox_count_host_side():
+    lib = _lib.load()
+    expect = {"v2": 8732, "v2_512": 24564, "v2_custom": 11620, "v2_custom_512": 32756,
+              "v2_custom_squareonly": 8732, "v1": 7308}
+    for name, p in expect.items():
+        assert lib.gssd_priorbox_count(_lib.prior_cfg(config.ALL[name])) == p
+    bad = dict(config.v2); bad["variance"] = [0.1, -1]
+    assert lib.gssd_priorbox_count(_lib.prior_cfg(bad)) == _lib.ERR_VALUE
+
+
+def test_argument_errors_are_reported_before_any_launch():
+    lib = _lib.load()
+    assert lib.gssd_detect(None, None, None, 1, 1, 2, 200, 0.1, 0.45, 0.1, 0.2, None, None, None, None) == _lib.ERR_ARG
+    assert lib.gssd_detect(1, 1, 1, 1, 10, 2, 200, 0.1, 0.0, 0.1, 0.2, 1, None, None, None) == _lib.ERR_VALUE
+    assert lib.gssd_detect(1, 1, 1, 1, 10 ** 6, 2, 200, 0.1, 0.45, 0.1, 0.2, 1, None, None, None) == _lib.ERR_LIMIT
+    assert lib.gssd_match(1, 100, 1, 1, 2, 0, 0, 0.5, 0.1, 0.2, 1, 1, None, None, 0, None) == _lib.ERR_EMPTY
+    assert lib.gssd_match(1, 100, 1, 1, 2, 900, 500, 0.5, 0.1, 0.2, 1, 1, None, None, 0, None) == _lib.ERR_LIMIT
+    with pytest.raises(ValueError):
+        _lib.check(_lib.ERR_VALUE)
+    with pytest.raises(IndexError):
+        _lib.check(_lib.ERR_EMPTY)
+    with pytest.raises(RuntimeError):
+        _lib.check(_lib.ERR_WS)
+
+
+def test_layers_module_tree_mirrors_the_reference():
+    from grouped_ssd_pytorch_b200 import layers
+    from grouped_ssd_pytorch_b200.layers import Detect, L2Norm, MultiBoxLoss, PriorBox, box_utils
+    from grouped_ssd_pytorch_b200.layers.functions import Detect as D2, PriorBox as P2
+    from grouped_ssd_pytorch_b200.layers.modules import L2Norm as L2, MultiBoxLoss as M2
+    assert (D2, P2, L2, M2) == (Detect, PriorBox, L2Norm, MultiBoxLoss)
+    for fn in ("point_form", "center_size", "intersect", "jaccard", "match", "encode", "decode", "log_sum_exp", "nms"):
+        assert callable(getattr(box_utils, fn))
+    # signatures of the reference (box_utils.py:70,174; multibox_loss.py:31-33)
+    assert list(inspect.signature(box_utils.match).parameters) == [
+        "threshold", "truths", "priors", "variances", "labels", "loc_t", "conf_t", "idx"]
+    assert list(inspect.signature(box_utils.nms).parameters) == ["boxes", "scores", "overlap", "top_k"]
+    assert list(inspect.signature(MultiBoxLoss.__init__).parameters)[1:] == [
+        "num_classes", "overlap_thresh", "prior_for_matching", "bkg_label", "neg_mining", "neg_pos",
+        "neg_overlap", "encode_target", "use_gpu"]
+    crit = MultiBoxLoss(2, 0.5, True, 0, True, 3, 0.5, False, True)      # train_lesion_multiphase_v2.py:639
+    assert crit.variance == [0.1, 0.2] and crit.negpos_ratio == 3 and crit.threshold == 0.5
+    assert layers.__name__.endswith("layers")
+
+
+def test_install_as_layers_resolves_reference_imports():
+    saved = {k: sys.modules.get(k) for k in ("layers", "layers.box_utils", "layers.functions", "layers.modules", "data")}
+    try:
+        for k in saved:
+            sys.modules.pop(k, None)
+        pkg.install_as_layers()
+        ns = {}
+        exec("from layers import *\nfrom layers.modules import MultiBoxLoss\nfrom layers.box_utils import match, nms\n"
+             "from data import v2", ns)
+        assert ns["v2"]["name"] == "v2" and "Detect" in ns and "PriorBox" in ns and "L2Norm" in ns
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_reference_visible_errors_without_gpu_work():
+    from grouped_ssd_pytorch_b200.layers import Detect, PriorBox
+    bad = dict(config.v2); bad["variance"] = [0.0, 0.2]
+    with pytest.raises(ValueError):
+        PriorBox(bad)                                            # prior_box.py:28-30
+    with pytest.raises(ValueError):
+        Detect(2, 0, 200, 0.01, 0.0)                             # detection.py:19-20
+    with pytest.raises(ValueError):
+        Detect.apply(2, 0, 200, 0.01, 0.0, torch.zeros(1, 4, 4), torch.zeros(1, 4, 2), torch.zeros(4, 4))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only box behaviour")
+def test_no_cpu_fallback():
+    from grouped_ssd_pytorch_b200.layers import MultiBoxLoss, PriorBox, box_utils
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        PriorBox(config.v2).forward()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        box_utils.jaccard(torch.rand(2, 4), torch.rand(3, 4))
+    crit = MultiBoxLoss(2, 0.5, True, 0, True, 3, 0.5, False, False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        crit((torch.zeros(1, 4, 4), torch.zeros(1, 4, 2), torch.rand(4, 4)), [torch.rand(1, 5)])
+
+
+def test_product_never_imports_the_oracle():
+    pkg_dir = os.path.dirname(pkg.__file__)
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower() or f == "synthetic.py", os.path.join(dirpath, f)
+
+
+def test_synthetic_inputs_are_reproducible():
+    from grouped_ssd_pytorch_b200 import synthetic as syn
+    a = syn.targets(syn.rng(5), 4)
+    b = syn.targets(syn.rng(5), 4)
+    assert all((x == y).all() for x, y in zip(a, b))
+    assert all(1 <= t.shape[0] <= 5 and t.shape[1] == 5 and (t[:, 2] >= t[:, 0]).all() for t in a)
+    s = syn.detect_scores(syn.rng(1), 2, 1000, 2, -4.0)
+    assert 0.005 < (s[..., 1] > 0.2).mean() < 0.08

@@ -1,0 +1,402 @@
+"""GPU parity: libgssd_b200.so (through the reference-shaped Python API and the C ABI under it)
+against the CPU oracle and the reference's golden outputs.  Bit-exact for indices / labels / masks /
+keep lists; 1e-5 relative for float outputs (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from grouped_ssd_pytorch_b200 import config as cfg
+from grouped_ssd_pytorch_b200 import synthetic as syn
+from grouped_ssd_pytorch_b200.layers import Detect, L2Norm, MultiBoxLoss, PriorBox, box_utils as BU
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5          # stated tolerance for fp32 outputs
+T = torch.from_numpy
+
+
+def cu(a):
+    return T(np.ascontiguousarray(a)).cuda()
+
+
+def close(a, b, rtol=RTOL, atol=1e-7):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+def eq(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+    assert a.shape == b.shape
+    bad = np.flatnonzero(a.reshape(-1) != b.reshape(-1))
+    assert bad.size == 0, "%d mismatches, first at %s: %s vs %s" % (bad.size, bad[:5], a.reshape(-1)[bad[:5]], b.reshape(-1)[bad[:5]])
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["v2", "v2_512", "v2_custom", "v2_custom_512", "v2_custom_squareonly", "v1"])
+def test_priorbox_bit_exact(name):
+    got = PriorBox(cfg.ALL[name]).forward()
+    assert got.device.type == "cpu" and got.dtype == torch.float32
+    ref = cases.priors(name)
+    eq(got.numpy().view(np.uint32), ref.view(np.uint32))
+
+
+def test_priorbox_noclip_and_errors():
+    c = cases.small_cfg(); c["clip"] = False
+    eq(PriorBox(c).forward().numpy(), cases.priors("small_noclip"))
+    bad = dict(cfg.v2); bad["variance"] = [0.1, 0.0]
+    with pytest.raises(ValueError):
+        PriorBox(bad)
+
+
+def test_box_utils_elementwise():
+    g = cases.golden("box_utils")
+    pri, a = cu(g["priors"]), cu(g["a"])
+    pf = BU.point_form(pri)
+    eq(pf, g["point_form"])
+    eq(BU.intersect(a, pf), g["intersect"])
+    eq(BU.jaccard(a, pf), g["jaccard"])
+    close(BU.encode(cu(g["matched"]), pri, cases.VAR), g["encode"])
+    close(BU.decode(cu(g["loc"]), pri, cases.VAR), g["decode"])
+    close(BU.log_sum_exp(cu(g["x"])), g["log_sum_exp"])
+    close(BU.center_size(pf), g["priors"], rtol=1e-6)
+    # CPU tensors in -> CPU tensors out
+    out = BU.jaccard(T(g["a"]), T(g["point_form"]))
+    assert out.device.type == "cpu"
+    eq(out, g["jaccard"])
+
+
+def _match_one(t, pri, thr=0.5):
+    P = pri.shape[0]
+    loc_t = torch.zeros(2, P, 4, device="cuda")
+    conf_t = torch.zeros(2, P, dtype=torch.long, device="cuda")
+    BU.match(thr, cu(t[:, :4]), cu(pri), cases.VAR, cu(t[:, 4]), loc_t, conf_t, 1)
+    assert float(loc_t[0].abs().sum()) == 0 and int(conf_t[0].sum()) == 0
+    return loc_t[1], conf_t[1]
+
+
+def test_match_random_v2_vs_golden_and_oracle():
+    g = cases.golden("match")
+    pri = cases.priors("v2")
+    tg = cases.match_rand_targets()
+    loc_b, conf_b, bti_b = BU.match_batch(0.5, [cu(t) for t in tg], cu(pri), cases.VAR, return_idx=True)
+    for i, t in enumerate(tg):
+        loc_t, conf_t = _match_one(t, pri)
+        eq(conf_t, g["rand%d_conf_t" % i].astype(np.int64))
+        eq(conf_b[i], g["rand%d_conf_t" % i].astype(np.int64))
+        eq(bti_b[i], g["rand%d_bti" % i].astype(np.int32))
+        o = O.match(0.5, t[:, :4], pri, cases.VAR, t[:, 4])
+        close(loc_t, o["loc_t"])
+        close(loc_b[i], o["loc_t"])
+        if i == 0:
+            close(loc_t, g["rand0_loc_t"])
+
+
+def test_match_cpu_target_tensors():
+    """the reference fills CPU loc_t / conf_t (multibox_loss.py:65-66): in-place semantics must hold."""
+    g = cases.golden("match")
+    pri = cases.priors("v2")
+    t = cases.match_rand_targets()[0]
+    loc_t = torch.zeros(1, pri.shape[0], 4)
+    conf_t = torch.zeros(1, pri.shape[0], dtype=torch.long)
+    BU.match(0.5, T(t[:, :4].copy()), T(pri), cases.VAR, T(t[:, 4].copy()), loc_t, conf_t, 0)
+    eq(conf_t[0], g["rand0_conf_t"].astype(np.int64))
+    close(loc_t[0], g["rand0_loc_t"])
+
+
+def test_match_stress_512():
+    g = cases.golden("match")
+    t = g["s512_targets"]
+    pri = cases.priors("v2_512")
+    loc_t, conf_t, bti = BU.match_batch(0.5, [cu(t)], cu(pri), cases.VAR, return_idx=True)
+    eq(conf_t[0], g["s512_conf_t"].astype(np.int64))
+    eq(bti[0], g["s512_bti"].astype(np.int32))
+    close(loc_t[0][conf_t[0] > 0], g["s512_loc_t_pos"])
+
+
+@pytest.mark.parametrize("case", ["shared", "zero_iou", "exact", "all_tie", "thr"])
+def test_match_edges(case):
+    g = cases.golden("match")
+    t = g["edge_%s_targets" % case]
+    pri = g["edge_thr_priors"] if case == "thr" else g["small_priors"]
+    loc_t, conf_t, bti = BU.match_batch(0.5, [cu(t)], cu(pri), cases.VAR, return_idx=True)
+    eq(conf_t[0], g["edge_%s_conf_t" % case].astype(np.int64))
+    eq(bti[0], g["edge_%s_bti" % case].astype(np.int32))
+    ref = g["edge_%s_loc_t" % case]
+    got = loc_t[0].cpu().numpy()
+    fin = np.isfinite(ref)
+    eq(np.isfinite(got), fin)
+    close(got[fin], ref[fin])
+
+
+def test_match_empty_raises():
+    pri = cu(cases.priors("small"))
+    with pytest.raises(IndexError):
+        BU.match_batch(0.5, [torch.zeros(0, 5).cuda()], pri, cases.VAR)
+
+
+@pytest.mark.parametrize("B,gmax,pname", [(1, 5, "v2"), (8, 5, "v2"), (40, 12, "v2"), (3, 32, "v2_512"),
+                                          (300, 3, "small"), (5, 100, "v2_custom_512")])
+def test_match_batched_vs_oracle(B, gmax, pname):
+    """every cluster configuration (8/4/2/1 CTAs per image) and ragged G"""
+    pri = cases.priors(pname)
+    tg = syn.targets(syn.rng(100 + B), B, 1, gmax)
+    loc_t, conf_t, bti = BU.match_batch(0.5, [cu(t) for t in tg], cu(pri), cases.VAR, return_idx=True)
+    for i in range(0, B, max(1, B // 6)):
+        o = O.match(0.5, tg[i][:, :4], pri, cases.VAR, tg[i][:, 4])
+        eq(conf_t[i], o["conf_t"]); eq(bti[i], o["best_truth_idx"]); close(loc_t[i], o["loc_t"])
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_loss(loc, conf, pri, tg, C, ratio, masks=True, cpu_targets=False):
+    crit = MultiBoxLoss(C, 0.5, True, 0, True, ratio, 0.5, False, True)
+    crit.keep_masks = masks
+    l = cu(loc).requires_grad_()
+    c = cu(conf).requires_grad_()
+    targets = [T(t) if cpu_targets else cu(t) for t in tg]
+    ll, lc = crit((l, c, cu(pri)), targets)
+    (ll + lc).backward()
+    return ll, lc, l.grad, c.grad, crit.last_masks
+
+
+def check_loss_against_oracle(loc, conf, pri, tg, C, ratio, res):
+    ll, lc, gl, gc, m = res
+    o = O.multibox_loss(loc, conf, pri, tg, 0.5, ratio, cases.VAR)
+    eq(m["num_pos"], o["num_pos"])
+    eq(m["pos"], o["pos"])                                       # positive mask: bit-exact
+    # hard-negative mask: bit-exact unless two keys tie (or nearly tie: CUDA vs glibc expf/logf
+    # differ in the last ulp) at the num_neg cut of that image
+    neg = m["neg"].cpu().numpy()
+    n_checked = 0
+    for b in range(loc.shape[0]):
+        nn = min(ratio * int(o["num_pos"][b]), pri.shape[0] - 1)
+        ks = np.sort(o["key"][b])[::-1]
+        near = nn < pri.shape[0] and (ks[nn - 1] - ks[nn]) <= 4e-6 * max(1.0, abs(ks[nn]))
+        if not near:
+            eq(neg[b], o["neg"][b]); n_checked += 1
+        else:
+            # only priors whose key is within the tolerance of the cut value may differ
+            diff = neg[b] != o["neg"][b]
+            assert (np.abs(o["key"][b][diff] - ks[nn]) <= 4e-6 * max(1.0, abs(ks[nn]))).all()
+            assert neg[b].sum() == o["neg"][b].sum()
+    close(ll, o["loss_l"]); close(lc, o["loss_c"])
+    close(gl, o["grad_loc"], atol=1e-9)
+    same = (neg == o["neg"]).all(1)
+    close(gc[T(same).cuda()], o["grad_conf"][same], atol=1e-9)
+    return n_checked
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_multibox_loss_golden(tag):
+    g = cases.golden("loss")
+    loc, conf, pri, tg, C, ratio = cases.loss_case(tag)
+    res = run_loss(loc, conf, pri, tg, C, ratio)
+    assert check_loss_against_oracle(loc, conf, pri, tg, C, ratio, res) >= 1
+    ll, lc, gl, gc, m = res
+    close(torch.stack([ll, lc]), g[tag + "_loss"].astype(np.float32))
+    if tag == "c":
+        ref_gl, ref_gc = g["c_grad_loc"], g["c_grad_conf"]
+    else:
+        ref_gl = cases.dense_grads(g, tag + "_grad_loc", loc.shape)
+        ref_gc = cases.dense_grads(g, tag + "_grad_conf", conf.shape)
+    eq((gl != 0).cpu().numpy(), ref_gl != 0)
+    close(gl, ref_gl, atol=1e-9)
+    o = O.multibox_loss(loc, conf, pri, tg, 0.5, ratio, cases.VAR)
+    stable = cases.ohnm_unambiguous(o["key"], o["pos"], ratio)
+    same = (m["neg"].cpu().numpy() == o["neg"]).all(1) & stable
+    assert same.any()
+    close(gc[T(same).cuda()], ref_gc[same], atol=1e-9)
+
+
+@pytest.mark.parametrize("B,gmax,pname,C", [(1, 5, "v2", 2), (32, 5, "v2", 2), (50, 8, "v2", 2), (160, 5, "v2", 2),
+                                            (310, 3, "small", 2), (6, 32, "v2_512", 2), (4, 6, "v2", 4)])
+def test_multibox_loss_vs_oracle(B, gmax, pname, C):
+    pri = cases.priors(pname)
+    r = syn.rng(200 + B)
+    tg = syn.targets(r, B, 1, gmax)
+    if C > 2:
+        for t in tg:
+            t[:, 4] = r.randint(0, C - 1, size=t.shape[0])
+    loc, conf = syn.loc(r, B, pri.shape[0]), syn.conf_logits(r, B, pri.shape[0], C)
+    res = run_loss(loc, conf, pri, tg, C, 3)
+    assert check_loss_against_oracle(loc, conf, pri, tg, C, 3, res) >= max(1, B // 2)
+
+
+def test_multibox_loss_key_ties_at_cut():
+    """exact duplicate keys straddling the num_neg cut: lower prior index first (the oracle's stable
+    rule); plus saturated rows whose key underflows to 0 and ties with the zeroed positives."""
+    pri = cases.priors("small")
+    P = pri.shape[0]
+    r = syn.rng(77)
+    tg = syn.targets(r, 3, 2, 3)
+    loc = syn.loc(r, 3, P)
+    conf = np.zeros((3, P, 2), np.float32)
+    conf[0, :, 1] = np.repeat(np.arange(P // 8 + 1), 8)[:P] * 0.25      # blocks of 8 equal keys
+    conf[1] = syn.conf_logits(r, 1, P, 2)[0]
+    conf[1, ::2] = np.array([40.0, -40.0], np.float32)                   # key == 0 exactly
+    conf[2, :, 1] = 1.0                                                  # every key identical
+    res = run_loss(loc, conf, pri, tg, 2, 3)
+    o = O.multibox_loss(loc, conf, pri, tg, 0.5, 3, cases.VAR)
+    eq(res[4]["pos"], o["pos"])
+    eq(res[4]["neg"], o["neg"])
+    close(res[1], o["loss_c"]); close(res[3], o["grad_conf"], atol=1e-9)
+
+
+def test_multibox_loss_api_variants():
+    loc, conf, pri, tg, C, ratio = cases.loss_case("a")
+    base = run_loss(loc, conf, pri, tg, C, ratio)
+    # CPU target tensors (the usual DataLoader output) and CPU priors (what GSSD.forward returns)
+    crit = MultiBoxLoss(C, 0.5, True, 0, True, ratio, 0.5, False, True)
+    ll, lc = crit((cu(loc), cu(conf), T(pri)), [T(t) for t in tg])
+    eq(torch.stack([ll, lc]), torch.stack(base[:2]).detach().cpu().numpy())
+    assert not ll.requires_grad
+    # upstream gradients other than 1 are honoured
+    l = cu(loc).requires_grad_(); c = cu(conf).requires_grad_()
+    ll, lc = crit((l, c, cu(pri)), [cu(t) for t in tg])
+    (2.0 * ll + 0.5 * lc).backward()
+    close(l.grad, 2.0 * base[2].cpu().numpy(), rtol=1e-6, atol=1e-12)
+    close(c.grad, 0.5 * base[3].cpu().numpy(), rtol=1e-6, atol=1e-12)
+    with pytest.raises(IndexError):
+        crit((cu(loc), cu(conf), cu(pri)), [cu(tg[0]), torch.zeros(0, 5).cuda(), cu(tg[2]), cu(tg[3])])
+
+
+def test_multibox_loss_deterministic():
+    loc, conf, pri, tg, C, ratio = cases.loss_case("a")
+    a = run_loss(loc, conf, pri, tg, C, ratio)
+    b = run_loss(loc, conf, pri, tg, C, ratio)
+    for x, y in zip(a[:4], b[:4]):
+        assert torch.equal(x, y)
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_nms_golden(tag):
+    g = cases.golden("nms")
+    n, ov, k = g[tag + "_args"]
+    n, k = int(n), int(k)
+    keep, count = BU.nms(cu(g["boxes"][:n]), cu(g["scores"][:n]), float(ov), k)
+    assert isinstance(count, int) and count == int(g[tag + "_count"])
+    assert keep.dtype == torch.int64
+    eq(keep, g[tag + "_keep"])
+
+
+def test_nms_edge_cases():
+    out = BU.nms(torch.zeros(0, 4).cuda(), torch.zeros(0).cuda())
+    assert isinstance(out, torch.Tensor) and out.numel() == 0          # box_utils.py:187-188: bare tensor
+    r = syn.rng(5)
+    c = r.uniform(0.3, 0.7, size=(400, 2)); wh = r.uniform(0.1, 0.3, size=(400, 2))
+    boxes = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    scores = (r.randint(0, 6, size=400) / 8.0).astype(np.float32)        # many exactly equal scores
+    for top_k in (1, 7, 64, 200, 1000):
+        for ov in (0.1, 0.45, 0.9):
+            keep, count = BU.nms(cu(boxes), cu(scores), ov, top_k)
+            ok, oc, _ = O.nms(boxes, scores, ov, top_k)
+            assert count == oc
+            eq(keep, ok)
+    # CPU in -> CPU out
+    keep, count = BU.nms(T(boxes), T(scores), 0.45, 200)
+    assert keep.device.type == "cpu"
+    ok, oc, _ = O.nms(boxes, scores, 0.45, 200)
+    assert count == oc
+    eq(keep, ok)
+    # degenerate: zero-area and identical boxes (IoU = 0/0 -> NaN -> removed, box_utils.py:237)
+    boxes2 = np.array([[0.5, 0.5, 0.5, 0.5]] * 4 + [[0.1, 0.1, 0.2, 0.2]] * 3, np.float32)
+    scores2 = np.array([0.9, 0.8, 0.7, 0.6, 0.5, 0.5, 0.4], np.float32)
+    keep, count = BU.nms(cu(boxes2), cu(scores2), 0.45, 200)
+    ok, oc, _ = O.nms(boxes2, scores2, 0.45, 200)
+    assert count == oc
+    eq(keep, ok)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_detect_golden(tag):
+    g = cases.golden("detect")
+    loc, conf, pri, C, thr = cases.detect_case(tag)
+    out = Detect.apply(C, 0, 200, thr, 0.45, cu(loc), cu(conf), cu(pri))
+    ref = g[tag + "_out"]
+    assert out.shape == ref.shape and out.is_cuda
+    o = O.detect(loc, conf, pri, C, 200, thr, 0.45, cases.VAR)
+    assert o["margin"].min() > 1e-5           # no decision within float noise of a threshold
+    eq(out[..., 0], ref[..., 0])               # scores are copied bits: same candidates, same keep list
+    close(out[..., 1:], ref[..., 1:])
+    out2, count, keep = Detect.apply_with_indices(C, 0, 200, thr, 0.45, cu(loc), cu(conf), cu(pri))
+    eq(count, o["count"]); eq(keep, o["keep_idx"])
+    legacy = Detect(C, 0, 200, thr, 0.45)(cu(loc), cu(conf), cu(pri))
+    assert torch.equal(legacy, out)
+    inst = Detect().apply(C, 0, 200, thr, 0.45, cu(loc), cu(conf), cu(pri))   # models/...group.py:75,384
+    assert torch.equal(inst, out)
+
+
+def test_detect_errors_and_devices():
+    loc, conf, pri, C, thr = cases.detect_case("a")
+    with pytest.raises(ValueError):
+        Detect.apply(C, 0, 200, thr, 0.0, cu(loc), cu(conf), cu(pri))
+    with pytest.raises(ValueError):
+        Detect(C, 0, 200, thr, -1.0)
+    out = Detect.apply(C, 0, 200, thr, 0.45, T(loc), T(conf), T(pri))
+    assert out.device.type == "cpu"
+    eq(out[..., 0], cases.golden("detect")["a_out"][..., 0])
+
+
+@pytest.mark.parametrize("B,pname,C,shift,sigma,thr,top_k", [
+    (16, "v2", 2, 0.0, 0.05, 0.2, 200),        # dense + clustered: real suppression, n_cand >> top_k
+    (16, "v2", 2, -4.0, 0.5, 0.2, 200),        # sparse-realistic
+    (4, "v2_512", 2, 0.0, 0.05, 0.2, 200),     # SSD512 prior set
+    (2, "v2", 5, -1.0, 0.1, 0.05, 64),         # several classes, other top_k
+    (2, "v2_custom_512", 2, 0.0, 0.05, 0.5, 1000),
+    (3, "small", 2, 0.0, 0.3, 0.1, 200),       # n_cand < top_k
+])
+def test_detect_vs_oracle(B, pname, C, shift, sigma, thr, top_k):
+    pri = cases.priors(pname)
+    r = syn.rng(300 + B)
+    loc = syn.loc(r, B, pri.shape[0], sigma)
+    conf = syn.detect_scores(r, B, pri.shape[0], C, shift)
+    out, count, keep = Detect.apply_with_indices(C, 0, top_k, thr, 0.45, cu(loc), cu(conf), cu(pri))
+    o = O.detect(loc, conf, pri, C, top_k, thr, 0.45, cases.VAR)
+    out, count, keep = out.cpu().numpy(), count.cpu().numpy(), keep.cpu().numpy()
+    n_exact = 0
+    for b in range(B):
+        for cl in range(C):
+            if o["margin"][b, cl] > 1e-5:      # decoded boxes differ by an ulp (expf): skip knife-edge IoUs
+                eq(keep[b, cl], o["keep_idx"][b, cl]); assert count[b, cl] == o["count"][b, cl]
+                eq(out[b, cl, :, 0], o["out"][b, cl, :, 0])
+                close(out[b, cl, :, 1:], o["out"][b, cl, :, 1:])
+                n_exact += 1
+    assert n_exact >= B * C * 0.8
+
+
+def test_detect_equal_scores():
+    """exactly equal scores at the top_k cut and inside the list: higher prior index first"""
+    pri = cases.priors("v2")
+    P = pri.shape[0]
+    r = syn.rng(9)
+    loc = syn.loc(r, 2, P, 0.05)
+    conf = np.zeros((2, P, 2), np.float32)
+    conf[..., 1] = (r.randint(1, 9, size=(2, P)) / 10.0).astype(np.float32)
+    conf[..., 0] = 1 - conf[..., 1]
+    out, count, keep = Detect.apply_with_indices(2, 0, 200, 0.2, 0.45, cu(loc), cu(conf), cu(pri))
+    o = O.detect(loc, conf, pri, 2, 200, 0.2, 0.45, cases.VAR)
+    assert o["margin"].min() > 1e-5
+    eq(keep, o["keep_idx"]); eq(count, o["count"])
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_l2norm_forward_backward():
+    g = cases.golden("l2norm")
+    m = L2Norm(64, 20).cuda()
+    with torch.no_grad():
+        m.weight.copy_(cu(g["weight"]))
+    x = cu(g["x"]).requires_grad_()
+    y = m(x)
+    close(y, g["y"])
+    close(y, O.l2norm(g["x"], g["weight"]))
+    y.backward(cu(g["gy"]))
+    close(x.grad, g["gx"], rtol=1e-4, atol=1e-6)
+    close(m.weight.grad, g["gw"], rtol=1e-4, atol=1e-5)
+    assert [k for k, _ in m.state_dict().items()] == ["weight"]
+    # the GSSD shape: conv4_3 map 512 x 38 x 38
+    r = syn.rng(3)
+    x = r.standard_normal((2, 512, 38, 38)).astype(np.float32)
+    w = np.full(512, 20, np.float32)
+    m = L2Norm(512, 20).cuda()
+    close(m(cu(x)), O.l2norm(x, w))
