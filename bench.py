@@ -1,0 +1,462 @@
+#!/usr/bin/env python
+"""bench.py — GSSD multibox hot path (match + OHNM loss fwd/bwd + Detect/NMS), images/sec.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+
+A step = one pass of the hot path over one batch: MultiBoxLoss forward + backward (2 kernels + the
+backward rescale) and Detect (1 kernel) on `--batch` images per GPU (BASELINE.json configs[1]:
+batch 32, SSD300 priors P=8732, 1-5 GT boxes per image, C=2).  Weak scaling: the per-GPU batch is
+fixed; every rank owns its own images, the only exchange is the 16-byte loss-statistics all-gather.
+
+value : inputs resident in HBM, a ring of input sets larger than L2, CUDA-graph replay of the public
+        API calls, CUDA-event timing, max over ranks.
+e2e   : the same step through the public Python API from pinned HOST buffers: H2D of loc / conf /
+        scores / targets, kernels, D2H of the two losses and of the Detect output, every step.
+roofline: the dominant kernel, timed alone with CUDA events inside this run, against
+        MEASURED_PEAKS.json (hbm_gbs).   cpu_baseline: the CPU oracle (port of the reference
+        algorithm, OpenMP over images) on the box's host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "GSSD images/sec (match+OHNM loss+Detect/NMS)"
+UNIT = "images/s"
+TOP_K, CONF_THRESH, NMS_THRESH, NEGPOS, MATCH_THRESH = 200, 0.2, 0.45, 3, 0.5
+L2_BYTES = 126e6
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU (configs[1]: 32)")
+    ap.add_argument("--priors", default="v2", help="prior-box config (v2: P=8732, v2_512: P=24564)")
+    ap.add_argument("--gmax", type=int, default=5, help="GT boxes per image ~ U{1..gmax}")
+    ap.add_argument("--no-graph", action="store_true", help="time eager API calls instead of CUDA-graph replay")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="also report the kernels' roofline at larger batches")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "configs[1]: GSSD multibox head, batch %d/GPU, %s priors, 1-%d GT, C=2, loss fwd+bwd + Detect(thr %.1f, top_k %d, nms %.2f)" % (
+        a.batch, a.priors, a.gmax, CONF_THRESH, TOP_K, NMS_THRESH)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------
+# synthetic inputs (numpy, seeded; the same generator the tests and the golden fixtures use)
+def make_inputs(a, rank, n_sets):
+    from grouped_ssd_pytorch_b200 import synthetic as syn
+    r = syn.rng(syn.SEED + 1000 * rank)
+    sets = []
+    for _ in range(n_sets):
+        tg = syn.targets(r, a.batch, 1, a.gmax)
+        loc = syn.loc(r, a.batch, a.P)
+        conf = syn.conf_logits(r, a.batch, a.P, 2)
+        x = conf.copy()
+        x[..., 1] -= 4.0                                  # "sparse-realistic" Detect scores
+        sets.append(dict(targets=tg, loc=loc, conf=conf, scores=syn.softmax(x)))
+    return sets
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm on the host cores
+def cpu_step_fn(a, priors_np):
+    from oracle import oracle as O
+    O.lib()
+
+    def step(s):
+        O.multibox_loss(s["loc"], s["conf"], priors_np, s["targets"], MATCH_THRESH, NEGPOS, (0.1, 0.2), grads=True, extras=False)
+        O.detect(s["loc"], s["scores"], priors_np, 2, TOP_K, CONF_THRESH, NMS_THRESH, (0.1, 0.2))
+    return step
+
+
+def time_cpu(a, priors_np, sets, steps, warmup, budget_s):
+    step = cpu_step_fn(a, priors_np)
+    for i in range(max(1, warmup)):
+        step(sets[i % len(sets)])
+    t0 = time.perf_counter()
+    done = 0
+    while done < steps:
+        step(sets[done % len(sets)])
+        done += 1
+        if budget_s and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done, dt
+
+
+def run_reference(a):
+    """--impl reference: the reference algorithm (CPU oracle port, all host threads) on our config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from grouped_ssd_pytorch_b200 import config
+    from oracle import oracle as O
+    priors_np = O.priorbox(config.ALL[a.priors])
+    a.P = priors_np.shape[0]
+    sets = make_inputs(a, 0, 4)
+    cores = os.cpu_count() or 1
+    done, dt = time_cpu(a, priors_np, sets, a.steps, min(a.warmup, 3), budget_s=120.0)
+    v = done * a.batch / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": done,
+        "warmup": a.warmup, "ms_per_step": dt / done * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "batch_per_gpu": a.batch, "num_priors": a.P,
+                   "note": "reference algorithm as the CPU oracle port (oracle/gssd_oracle.c, OpenMP over images); "
+                           "the reference itself is Python/torch and is not present on the GPU box"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d steps of the batch-%d workload (loss fwd+bwd + Detect)" % (done, a.batch)},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        self.f.close()
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            load = [v for v in sm if v >= 0.5 * max(mx)] or sm        # samples taken while kernels were running
+            out.update(sm_mhz=statistics.median(load), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                       samples=len(sm), samples_under_load=len(load))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from grouped_ssd_pytorch_b200 import _lib, config
+    from grouped_ssd_pytorch_b200.layers import Detect, MultiBoxLoss, PriorBox
+    from grouped_ssd_pytorch_b200.layers.box_utils import pack_target_list as pack_targets
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.require_cuda()
+
+    priors = PriorBox(config.ALL[a.priors]).forward(device="cuda")
+    a.P = P = priors.shape[0]
+    B = a.batch
+    per_set = B * P * (16 + 8 + 8 + 16 + 8)              # loc, conf, scores, grad_loc, grad_conf
+    n_sets = int(min(64, max(2, L2_BYTES * 1.5 // per_set + 1)))
+    host = make_inputs(a, rank, n_sets)
+
+    crit = MultiBoxLoss(2, MATCH_THRESH, True, 0, True, NEGPOS, 0.5, False, True)   # train_lesion_multiphase_v2.py:639
+    dsets = []
+    for s in host:
+        dsets.append(dict(loc=torch.from_numpy(s["loc"]).to(dev).requires_grad_(),
+                          conf=torch.from_numpy(s["conf"]).to(dev).requires_grad_(),
+                          scores=torch.from_numpy(s["scores"]).to(dev),
+                          targets=[torch.from_numpy(t).to(dev) for t in s["targets"]]))
+
+    def step_device(d):
+        d["loc"].grad = None; d["conf"].grad = None
+        ll, lc = crit((d["loc"], d["conf"], priors), d["targets"])
+        (ll + lc).backward()
+        out = Detect.apply(2, 0, TOP_K, CONF_THRESH, NMS_THRESH, d["loc"].detach(), d["scores"], priors)
+        return ll, lc, out
+
+    # ---- kernels per step + optional CUDA graphs -------------------------------------------------------
+    for d in dsets[:2]:
+        step_device(d)
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    step_device(dsets[0])
+    torch.cuda.synchronize()
+    kernels_per_step = _lib.launch_count() - n0
+
+    graphs, use_graph = None, not a.no_graph
+    if use_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for d in dsets:
+                    step_device(d)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graphs = []
+            pool = None
+            for d in dsets:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    d["result"] = step_device(d)
+                pool = pool or g.pool()
+                graphs.append(g)
+            torch.cuda.synchronize()
+        except Exception as e:                              # pragma: no cover
+            sys.stderr.write("bench: CUDA-graph capture failed (%s); timing eager calls\n" % e)
+            graphs, use_graph = None, False
+            torch.cuda.synchronize()
+
+    def run_step(i):
+        if graphs is not None:
+            graphs[i % n_sets].replay()
+        else:
+            step_device(dsets[i % n_sets])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: device-resident --------------------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_w = time.perf_counter()
+    i = 0
+    while i < max(3, a.warmup) or time.perf_counter() - t_w < 0.5:     # W steps and >= 0.5 s: clocks have ramped
+        run_step(i)
+        i += 1
+        if i % 64 == 0:
+            torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_launch0 = _lib.launch_count()
+    e0.record()
+    for i in range(a.steps):
+        run_step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    eager_launches = _lib.launch_count() - n_launch0
+    gpu_launches = kernels_per_step * a.steps if graphs is not None else eager_launches
+
+    # ---- end to end: host buffers in, losses + detections out, every step -----------------------------------
+    pin = []
+    for s in host[:min(4, n_sets)]:
+        pin.append(dict(loc=torch.from_numpy(s["loc"]).pin_memory(), conf=torch.from_numpy(s["conf"]).pin_memory(),
+                        scores=torch.from_numpy(s["scores"]).pin_memory(),
+                        targets=[torch.from_numpy(t) for t in s["targets"]]))
+    out_host = torch.empty((B, 2, TOP_K, 5), dtype=torch.float32).pin_memory()
+    loss_host = torch.empty((2,), dtype=torch.float32).pin_memory()
+
+    def step_e2e(h):
+        loc = h["loc"].to(dev, non_blocking=True).requires_grad_()
+        conf = h["conf"].to(dev, non_blocking=True).requires_grad_()
+        scores = h["scores"].to(dev, non_blocking=True)
+        ll, lc = crit((loc, conf, priors), h["targets"])        # targets: CPU tensors, packed + copied inside
+        (ll + lc).backward()
+        out = Detect.apply(2, 0, TOP_K, CONF_THRESH, NMS_THRESH, loc.detach(), scores, priors)
+        loss_host.copy_(torch.stack([ll.detach(), lc.detach()]), non_blocking=True)
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                # the step's results are on the host
+        return loss_host, out_host
+
+    h2d = B * P * (16 + 8 + 8) + sum(t.numel() * 4 for t in pin[0]["targets"]) + 4 * (B + 1)
+    d2h = 8 + B * 2 * TOP_K * 5 * 4
+    e2e_steps = max(10, min(a.steps, 200))
+    for i in range(3):
+        step_e2e(pin[i % len(pin)])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        step_e2e(pin[i % len(pin)])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+
+    # ---- per-kernel durations (CUDA events on the launch stream, GPU kept busy so launches never starve) ----
+    kern = time_kernels(a, lib, _lib, torch, dev, priors, dsets, pack_targets, B, P) if rank == 0 else None
+
+    # ---- max over ranks ---------------------------------------------------------------------------------------
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        hbm, hbm_src = peaks()
+        dom = max(kern, key=lambda k: k["us"])
+        roof = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["gbs"], "peak": hbm, "unit": "GB/s",
+                "frac": dom["gbs"] / hbm, "traffic": None, "peak_source": hbm_src,
+                "algorithmic_bytes_per_launch": dom["bytes"], "avg_launch_us": dom["us"],
+                "kernels": [{k: v for k, v in kk.items()} for kk in kern]}
+        line = {
+            "metric": METRIC, "value": world * B * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": max(3, a.warmup), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "batch_per_gpu": B, "global_batch": world * B, "num_priors": P,
+                       "num_classes": 2, "parallelism": "dp%d (batch-sharded, 16-byte stats all-gather)" % world,
+                       "l2_policy": "ring of %d distinct input sets (%.0f MB) > L2 (126 MB)" % (n_sets, n_sets * per_set / 1e6),
+                       "launch": "cuda-graph replay of the public API calls" if graphs is not None else "eager public API calls",
+                       "kernels_per_step": kernels_per_step},
+            "clocks": clocks,
+            "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": int(gpu_launches),
+            "roofline": roof,
+        }
+        if not a.no_cpu_baseline:
+            from oracle import oracle as O
+            priors_np = priors.cpu().numpy()
+            done, dt = time_cpu(a, priors_np, host, 10 ** 9, 1, a.cpu_seconds)
+            line["cpu_baseline"] = {"value": done * B / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": "%d steps of the batch-%d workload in %.1f s (oracle/gssd_oracle.c, OpenMP over images)" % (done, B, dt)}
+        if a.sweep:
+            line["roofline_sweep"] = sweep(a, lib, _lib, torch, dev, pack_targets)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def time_kernels(a, lib, _lib, torch, dev, priors, dsets, pack_targets, B, P, iters=None):
+    """Average duration of each of our kernels, timed alone: a spin kernel keeps the GPU busy while the
+    CPU enqueues [event, kernel, event] x n, so no launch ever waits for the host."""
+    n_sets = len(dsets)
+    iters = iters or max(20, min(100, 4 * n_sets))
+    st = _lib.stream()
+    packed = [tuple(pack_targets(d["targets"], dev)) for d in dsets]
+    tags = torch.empty((B, P), dtype=torch.int16, device=dev)
+    stats = torch.empty((16 + 4 * B,), dtype=torch.uint8, device=dev)
+    losses = torch.empty((2,), dtype=torch.float32, device=dev)
+    gl = [torch.empty((B, P, 4), dtype=torch.float32, device=dev) for _ in range(n_sets)]
+    gc = [torch.empty((B, P, 2), dtype=torch.float32, device=dev) for _ in range(n_sets)]
+    wsb = lib.gssd_workspace_bytes(_lib.WS_LOSS, B, P, 2, 1, 0)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    out = torch.empty((B, 2, TOP_K, 5), dtype=torch.float32, device=dev)
+
+    def k_match(i):
+        gt, off, sg, gm = packed[i]
+        _lib.check(lib.gssd_mbox_match(priors.data_ptr(), P, dsets[i]["conf"].data_ptr(), 2, gt.data_ptr(), off.data_ptr(),
+                                       B, sg, gm, MATCH_THRESH, tags.data_ptr(), stats.data_ptr(), st))
+
+    def k_loss(i):
+        gt, off, sg, gm = packed[i]
+        _lib.check(lib.gssd_mbox_loss(dsets[i]["loc"].data_ptr(), dsets[i]["conf"].data_ptr(), priors.data_ptr(), B, P, 2,
+                                      gt.data_ptr(), off.data_ptr(), sg, gm, tags.data_ptr(), stats.data_ptr(), None, 0,
+                                      NEGPOS, 0.1, 0.2, losses.data_ptr(), gl[i].data_ptr(), gc[i].data_ptr(), None, None,
+                                      ws.data_ptr(), wsb, st))
+
+    def k_det(i):
+        _lib.check(lib.gssd_detect(dsets[i]["loc"].data_ptr(), dsets[i]["scores"].data_ptr(), priors.data_ptr(), B, P, 2,
+                                   TOP_K, CONF_THRESH, NMS_THRESH, 0.1, 0.2, out.data_ptr(), None, None, st))
+
+    res = []
+    specs = [("gssd_mbox_match (match_kernel: IoU sweep + conf max)", k_match, B * P * (16 + 8 + 2)),
+             ("gssd_mbox_loss (loss_kernel: encode + smooth-L1 + OHNM select + CE + grads)", k_loss, B * P * 64),
+             ("gssd_detect (detect_kernel: threshold + top-k + decode + NMS)", k_det, B * (P * 40 + 8000))]
+    k_match(0)
+    for name, fn, nbytes in specs:
+        for i in range(3):
+            fn(i % n_sets)
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        torch.cuda._sleep(int(2.5e7))                    # ~13 ms of GPU spin: the host runs ahead
+        for i in range(iters):
+            ev[i][0].record()
+            fn(i % n_sets)
+            ev[i][1].record()
+        torch.cuda.synchronize()
+        us = statistics.mean(e[0].elapsed_time(e[1]) for e in ev) * 1e3
+        res.append({"name": name, "us": us, "bytes": nbytes, "gbs": nbytes / us / 1e3})
+    return res
+
+
+def sweep(a, lib, _lib, torch, dev, pack_targets):
+    """The same three kernels at batches that fill the machine (configs[3]/[4] shapes, one GPU's share and
+    beyond): where the HBM roofline fraction of each kernel saturates."""
+    from grouped_ssd_pytorch_b200 import config, synthetic as syn
+    from grouped_ssd_pytorch_b200.layers import PriorBox
+    hbm, _ = peaks()
+    rows = []
+    for pname, B, gmax in (("v2", 256, 5), ("v2", 1024, 5), ("v2_512", 64, 32), ("v2_512", 512, 32)):
+        pri = PriorBox(config.ALL[pname]).forward(device="cuda")
+        P = pri.shape[0]
+        per_set = B * P * 56
+        n_sets = int(min(8, max(2, 200e6 // per_set + 1)))
+        r = syn.rng(7)
+        dsets = []
+        for _ in range(n_sets):
+            conf = torch.randn((B, P, 2), device=dev)
+            dsets.append(dict(loc=torch.randn((B, P, 4), device=dev) * 0.5, conf=conf,
+                              scores=torch.softmax(conf + torch.tensor([0.0, -4.0], device=dev), -1),
+                              targets=[torch.from_numpy(t).to(dev) for t in syn.targets(r, B, 1, gmax)]))
+        for k in time_kernels(a, lib, _lib, torch, dev, pri, dsets, pack_targets, B, P, iters=12):
+            rows.append({"priors": pname, "batch": B, "gmax": gmax, "kernel": k["name"].split(" ")[0], "us": k["us"],
+                         "gbs": k["gbs"], "frac": k["gbs"] / hbm})
+        del dsets
+        torch.cuda.empty_cache()
+    return rows
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -58,21 +58,113 @@ def jaccard(box_a, box_b):
     return _pair("gssd_jaccard", box_a, box_b)
 
 
+class _PinnedRing(object):
+    """Small ring of pinned host staging buffers for the per-step ground-truth upload.  A slot is reused
+    only after the copy that read it has completed (CUDA event); under CUDA-graph capture a fresh buffer
+    is allocated and kept alive instead, because the graph re-reads it at every replay."""
+
+    def __init__(self, slots=8):
+        self.bufs = [None] * slots
+        self.events = [None] * slots
+        self.i = 0
+        self.keep = []
+
+    def get(self, nbytes):
+        if torch.cuda.is_current_stream_capturing():
+            buf = torch.empty((max(nbytes, 16),), dtype=torch.uint8).pin_memory()
+            self.keep.append(buf)
+            return buf, None
+        k = self.i
+        self.i = (self.i + 1) % len(self.bufs)
+        if self.events[k] is not None:
+            self.events[k].synchronize()
+        if self.bufs[k] is None or self.bufs[k].numel() < nbytes:
+            self.bufs[k] = torch.empty((max(2 * nbytes, 4096),), dtype=torch.uint8).pin_memory()
+        return self.bufs[k], k
+
+    def sent(self, k):
+        if k is not None:
+            if self.events[k] is None:
+                self.events[k] = torch.cuda.Event()
+            self.events[k].record()
+
+
+_ring = _PinnedRing()
+
+
+class PackedTargets(object):
+    """Device image of the reference's `targets` list (multibox_loss.py:67-69): gt[sum_G,5] float32 rows
+    (xmin,ymin,xmax,ymax,label) and gt_off[B+1] int32 row offsets, plus the host-known sizes."""
+    __slots__ = ("gt", "gt_off", "sum_g", "g_max", "batch")
+
+    def __init__(self, gt, gt_off, sum_g, g_max, batch):
+        self.gt, self.gt_off, self.sum_g, self.g_max, self.batch = gt, gt_off, sum_g, g_max, batch
+
+    def __iter__(self):          # (gt, gt_off, sum_g, g_max) = pack_targets(...)
+        return iter((self.gt, self.gt_off, self.sum_g, self.g_max))
+
+
 def pack_targets(truths_list, labels_list, dev):
-    """per-image (truths[G,4], labels[G]) -> gt[sum_G,5] on `dev`, gt_off[B+1] int32 on `dev`,
-    sum_G, g_max.  Raises IndexError for an image without boxes (reference: box_utils.py:94)."""
-    offs = [0]
-    rows = []
-    for t, l in zip(truths_list, labels_list):
+    """per-image (truths[G,4], labels[G]) -> PackedTargets on `dev`.  One pinned-buffer H2D copy carries
+    the offsets (and the rows too when the targets live on the CPU); no host synchronisation.
+    Raises IndexError for an image without boxes (the reference fails at box_utils.py:94)."""
+    B = len(truths_list)
+    offs = [0] * (B + 1)
+    g_max = 0
+    for i, t in enumerate(truths_list):
         g = int(t.size(0)) if t.dim() > 0 else 0
         if g == 0:
             raise IndexError("match: an image has no ground-truth box")
-        offs.append(offs[-1] + g)
-        rows.append(torch.cat([t.detach().reshape(g, 4).float(), l.detach().reshape(g, 1).float()], 1))
-    gt = (rows[0] if len(rows) == 1 else torch.cat(rows, 0)).to(dev).contiguous()
-    gt_off = torch.tensor(offs, dtype=torch.int32).to(dev)
-    g_max = max(b - a for a, b in zip(offs[:-1], offs[1:]))
-    return gt, gt_off, offs[-1], g_max
+        offs[i + 1] = offs[i] + g
+        g_max = g if g > g_max else g_max
+    sum_g = offs[B]
+    on_cpu = not any(t.is_cuda for t in truths_list) and not any(l.is_cuda for l in labels_list)
+    n_rows = sum_g * 5 if on_cpu else 0
+    nbytes = 4 * (n_rows + B + 1)
+    buf, slot = _ring.get(nbytes)
+    host_i = buf[:nbytes].view(torch.int32)
+    host_i[n_rows:] = torch.tensor(offs, dtype=torch.int32)
+    if on_cpu:
+        host_f = buf[:4 * n_rows].view(torch.float32).view(sum_g, 5)
+        for i in range(B):
+            host_f[offs[i]:offs[i + 1], :4] = truths_list[i].detach().reshape(-1, 4)
+            host_f[offs[i]:offs[i + 1], 4] = labels_list[i].detach().reshape(-1)
+    staged = buf[:nbytes].to(dev, non_blocking=True)
+    _ring.sent(slot)
+    words = staged.view(torch.int32)
+    gt_off = words[n_rows:]
+    if on_cpu:
+        gt = staged[:4 * n_rows].view(torch.float32).view(sum_g, 5)
+    else:
+        rows = [torch.cat([t.detach().reshape(-1, 4).to(dev, torch.float32),
+                           l.detach().reshape(-1, 1).to(dev, torch.float32)], 1)
+                for t, l in zip(truths_list, labels_list)]
+        gt = (rows[0] if B == 1 else torch.cat(rows, 0)).contiguous()
+    return PackedTargets(gt, gt_off, sum_g, g_max, B)
+
+
+def pack_target_list(targets, dev):
+    """list of [n_i,5] tensors (the DataLoader format, data_custom_v2.py:260-263) -> PackedTargets."""
+    if isinstance(targets, PackedTargets):
+        return targets
+    if all((not t.is_cuda) for t in targets):
+        return pack_targets([t[:, :-1] for t in targets], [t[:, -1] for t in targets], dev)
+    # CUDA targets: one cat of the whole rows instead of one per image
+    B = len(targets)
+    offs = [0] * (B + 1)
+    g_max = 0
+    for i, t in enumerate(targets):
+        g = int(t.size(0)) if t.dim() > 0 else 0
+        if g == 0:
+            raise IndexError("match: an image has no ground-truth box")
+        offs[i + 1] = offs[i] + g
+        g_max = max(g_max, g)
+    buf, slot = _ring.get(4 * (B + 1))
+    buf[:4 * (B + 1)].view(torch.int32).copy_(torch.tensor(offs, dtype=torch.int32))
+    gt_off = buf[:4 * (B + 1)].to(dev, non_blocking=True).view(torch.int32)
+    _ring.sent(slot)
+    gt = torch.cat([t.detach().to(dev) for t in targets], 0).to(torch.float32).contiguous()
+    return PackedTargets(gt, gt_off, offs[B], g_max, B)
 
 
 def match(threshold, truths, priors, variances, labels, loc_t, conf_t, idx):
@@ -104,7 +196,7 @@ def match_batch(threshold, targets, priors, variances, return_idx=False):
     with torch.cuda.device(dev):
         pri = _lib.f32(priors, dev)
         P, B = pri.size(0), len(targets)
-        gt, gt_off, sum_g, g_max = pack_targets([t[:, :-1] for t in targets], [t[:, -1] for t in targets], dev)
+        gt, gt_off, sum_g, g_max = pack_target_list(targets, dev)
         loc_t = torch.empty((B, P, 4), dtype=torch.float32, device=dev)
         conf_t = torch.empty((B, P), dtype=torch.int64, device=dev)
         bti = torch.empty((B, P), dtype=torch.int32, device=dev) if return_idx else None

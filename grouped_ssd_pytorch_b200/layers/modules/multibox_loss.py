@@ -6,7 +6,7 @@ import torch.nn as nn
 
 from ... import _lib
 from ...config import v2 as cfg
-from ..box_utils import pack_targets
+from ..box_utils import pack_target_list
 
 
 def _dist_world():
@@ -62,6 +62,7 @@ class _MultiBoxLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_l, g_c, *_unused):
         grad_loc, grad_conf = ctx.grads
+        ctx.grads = None                       # hand the buffers over: autograd can adopt them without a copy
         if grad_loc is None:
             return (None,) * 12
         lib = _lib.load()
@@ -135,8 +136,8 @@ class MultiBoxLoss(nn.Module):
             if conf.dim() == 2:
                 conf = conf.view(num, -1, self.num_classes)
             pri = self._device_priors(priors, dev)
-            tl = [targets[i] for i in range(num)]
-            gt, gt_off, sum_g, g_max = pack_targets([t[:, :-1] for t in tl], [t[:, -1] for t in tl], dev)
+            gt, gt_off, sum_g, g_max = pack_target_list(
+                targets if not isinstance(targets, (list, tuple)) else [targets[i] for i in range(num)], dev)
             loss_l, loss_c, pos, neg, num_pos = _MultiBoxLossFn.apply(
                 loc, conf, pri, gt, gt_off, sum_g, g_max, self.threshold, self.negpos_ratio, self.variance,
                 self.keep_masks, self.process_group)

@@ -382,13 +382,14 @@ static int cmp_score_asc(const void *a, const void *b) {       /* stable ascendi
     return (x->idx > y->idx) - (x->idx < y->idx);
 }
 
-/* keep[n] zero padded; returns count.  min_margin (opt): smallest |IoU - overlap| over all
- * decisions taken and smallest score gap at the top_k cut — how close the result is to flipping. */
+/* keep[n] zero padded; returns count.  min_margin (opt, [2]): [0] = smallest |IoU - overlap| over all
+ * suppression decisions taken (how close the keep list is to flipping under 1-ulp box noise),
+ * [1] = score gap at the top_k cut (0 = an exact tie there: order undefined in the reference). */
 EXPORT int gssd_oracle_nms(const float *boxes, const float *scores, int n, float overlap, int top_k,
                            int64_t *keep, float *min_margin) {
     for (int i = 0; i < n; ++i) keep[i] = 0;                  /* 186 */
-    float margin = INFINITY;
-    if (n <= 0) { if (min_margin) *min_margin = margin; return 0; }   /* 187-188 */
+    float margin = INFINITY, cut_gap = INFINITY;
+    if (n <= 0) { if (min_margin) { min_margin[0] = margin; min_margin[1] = cut_gap; } return 0; }   /* 187-188 */
     float *area = (float *)malloc(sizeof(float) * (size_t)n);
     score_idx *si = (score_idx *)malloc(sizeof(score_idx) * (size_t)n);
     for (int i = 0; i < n; ++i) {
@@ -400,7 +401,7 @@ EXPORT int gssd_oracle_nms(const float *boxes, const float *scores, int n, float
     int m = n < top_k ? n : top_k;                            /* 196: idx[-top_k:] */
     int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)m);
     for (int i = 0; i < m; ++i) idx[i] = si[n - m + i].idx;
-    if (n > m) { float gap = si[n - m].s - si[n - m - 1].s; if (gap < margin) margin = gap; }
+    if (n > m) cut_gap = si[n - m].s - si[n - m - 1].s;
     int count = 0;
     while (m > 0) {                                           /* 206 */
         int i = idx[m - 1];                                   /* 207 */
@@ -426,7 +427,7 @@ EXPORT int gssd_oracle_nms(const float *boxes, const float *scores, int n, float
         m = w_out;
     }
     free(area); free(si); free(idx);
-    if (min_margin) *min_margin = margin;
+    if (min_margin) { min_margin[0] = margin; min_margin[1] = cut_gap; }
     return count;
 }
 
@@ -436,7 +437,7 @@ EXPORT int gssd_oracle_detect(const float *loc, const float *conf, const float *
                               int B, int P, int C, int top_k, float conf_thresh, float nms_thresh,
                               float v0, float v1, float *out /* [B,C,top_k,5] */,
                               int32_t *count_out /* [B,C] opt */, int32_t *keep_idx_out /* [B,C,top_k] opt */,
-                              float *min_margin /* [B,C] opt */) {
+                              float *min_margin /* [B,C] opt: IoU margin */, float *cut_gap /* [B,C] opt */) {
     if (nms_thresh <= 0) return GSSD_ERR_VALUE;               /* 39-40 */
     memset(out, 0, sizeof(float) * (size_t)B * C * top_k * 5);    /* 56 */
     if (keep_idx_out) for (size_t i = 0; i < (size_t)B * C * top_k; ++i) keep_idx_out[i] = -1;
@@ -457,10 +458,11 @@ EXPORT int gssd_oracle_detect(const float *loc, const float *conf, const float *
                     sc[n] = s; memcpy(bx + 4 * n, dec + 4 * p, 4 * sizeof(float)); orig[n] = p; ++n;
                 }
             }
-            float mg = INFINITY;
-            if (min_margin) min_margin[b * C + cl] = mg;
+            float mg[2] = {INFINITY, INFINITY};
+            if (min_margin) min_margin[b * C + cl] = mg[0];
+            if (cut_gap) cut_gap[b * C + cl] = mg[1];
             if (n == 0) continue;                             /* 73-75 */
-            int cnt = gssd_oracle_nms(bx, sc, n, nms_thresh, top_k, keep, &mg);   /* 81 */
+            int cnt = gssd_oracle_nms(bx, sc, n, nms_thresh, top_k, keep, mg);   /* 81 */
             float *o = out + (((size_t)b * C + cl) * top_k) * 5;
             for (int r = 0; r < cnt; ++r) {                   /* 82-84 */
                 o[5 * r] = sc[keep[r]];
@@ -468,7 +470,8 @@ EXPORT int gssd_oracle_detect(const float *loc, const float *conf, const float *
                 if (keep_idx_out) keep_idx_out[((size_t)b * C + cl) * top_k + r] = orig[keep[r]];
             }
             if (count_out) count_out[b * C + cl] = cnt;
-            if (min_margin) min_margin[b * C + cl] = mg;
+            if (min_margin) min_margin[b * C + cl] = mg[0];
+            if (cut_gap) cut_gap[b * C + cl] = mg[1];
         }
         free(dec); free(bx); free(sc); free(orig); free(keep);
     }

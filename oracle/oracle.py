@@ -210,10 +210,10 @@ def nms(boxes, scores, overlap=0.5, top_k=200):
     b, s = _f(boxes).reshape(-1, 4), _f(scores).reshape(-1)
     n = s.shape[0]
     keep = np.zeros((n,), np.int64)
-    margin = C.c_float(0)
+    margin = np.zeros(2, np.float32)
     cnt = lib().gssd_oracle_nms(_p(b), _p(s), C.c_int(n), C.c_float(overlap), C.c_int(top_k),
-                                _p(keep, C.c_int64), C.byref(margin))
-    return keep, cnt, margin.value
+                                _p(keep, C.c_int64), _p(margin))
+    return keep, cnt, float(min(margin[0], margin[1]))
 
 
 def detect(loc, conf, priors, num_classes, top_k, conf_thresh, nms_thresh, variances=(0.1, 0.2)):
@@ -222,16 +222,16 @@ def detect(loc, conf, priors, num_classes, top_k, conf_thresh, nms_thresh, varia
     out = np.empty((B, num_classes, top_k, 5), np.float32)
     count = np.empty((B, num_classes), np.int32)
     keep_idx = np.empty((B, num_classes, top_k), np.int32)
-    margin = np.empty((B, num_classes), np.float32)
-    margin[:] = np.inf
+    margin = np.full((B, num_classes), np.inf, np.float32)
+    cut_gap = np.full((B, num_classes), np.inf, np.float32)
     rc = lib().gssd_oracle_detect(_p(loc), _p(conf), _p(priors), C.c_int(B), C.c_int(P),
                                   C.c_int(num_classes), C.c_int(top_k), C.c_float(conf_thresh),
                                   C.c_float(nms_thresh), C.c_float(variances[0]), C.c_float(variances[1]),
-                                  _p(out), _p(count, C.c_int32), _p(keep_idx, C.c_int32), _p(margin))
+                                  _p(out), _p(count, C.c_int32), _p(keep_idx, C.c_int32), _p(margin), _p(cut_gap))
     if rc == -4:
         raise ValueError("nms_threshold must be non negative.")
     assert rc == 0, rc
-    return dict(out=out, count=count, keep_idx=keep_idx, margin=margin)
+    return dict(out=out, count=count, keep_idx=keep_idx, margin=margin, cut_gap=cut_gap)
 
 
 def l2norm(x, weight, eps=1e-10):

@@ -5,7 +5,7 @@ import numpy as np
 import torch
 from grouped_ssd_pytorch_b200 import _lib, config, synthetic as syn
 from grouped_ssd_pytorch_b200.layers import PriorBox
-from grouped_ssd_pytorch_b200.layers.box_utils import pack_targets
+from grouped_ssd_pytorch_b200.layers.box_utils import pack_target_list
 
 lib = _lib.require_cuda()
 dev = torch.device("cuda:0")
@@ -32,7 +32,7 @@ def run(pname, B, gmax):
     n_sets = max(2, min(12, int(300e6 // per_set) + 1))
     r = syn.rng(1)
     tg = syn.targets(r, B, 1, gmax)
-    gt, gt_off, sum_g, g_max = pack_targets([torch.from_numpy(t[:, :4]) for t in tg], [torch.from_numpy(t[:, 4]) for t in tg], dev)
+    gt, gt_off, sum_g, g_max = pack_target_list([torch.from_numpy(t) for t in tg], dev)
     locs = [torch.randn(B, P, 4, device=dev) * 0.5 for _ in range(n_sets)]
     confs = [torch.randn(B, P, 2, device=dev) for _ in range(n_sets)]
     scores = [torch.softmax(c + torch.tensor([0.0, -4.0], device=dev), -1) for c in confs]
