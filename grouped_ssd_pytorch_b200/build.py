@@ -39,15 +39,18 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, phase_timing=False):
+    """phase_timing=True builds libgssd_b200_dbg.so (clock64 stamps per kernel phase, development only)."""
+    lib = LIB.replace(".so", "_dbg.so") if phase_timing else LIB
+    if not force and not phase_timing and not stale():
         return LIB
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    extra = ["-DGSSD_PHASE_TIMING"] if phase_timing else []
     for s in SOURCES:
-        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
+        o = os.path.join(HERE, "build", s.replace(".cu", "_dbg.o" if phase_timing else ".o"))
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     failed = False
@@ -59,10 +62,10 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed building libgssd_b200.so")
     link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
-            "-Xcompiler", "-fPIC", "-o", LIB] + objs
+            "-Xcompiler", "-fPIC", "-o", lib] + objs
     subprocess.check_call(link)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, phase_timing="--phase-timing" in sys.argv))

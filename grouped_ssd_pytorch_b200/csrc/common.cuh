@@ -35,6 +35,46 @@ void note_launch(int n = 1);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Opt a kernel in to the full 227 KB of shared memory (static + dynamic) once per kernel and device.
+// (Keyed on the function address: all instantiations of one kernel template share a pointer TYPE.)
+static inline cudaError_t allow_max_smem(const void *kern) {
+    struct Entry { const void *fn; unsigned dev_mask; };
+    static Entry table[64];
+    static int n_entries = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    Entry *ent = nullptr;
+    for (int i = 0; i < n_entries; ++i) if (table[i].fn == kern) { ent = &table[i]; break; }
+    if (ent && dev < 32 && ((ent->dev_mask >> dev) & 1u)) return cudaSuccess;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return e;
+    int optin = 0;
+    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    if (e != cudaSuccess) return e;
+    if (!ent && n_entries < 64) { ent = &table[n_entries++]; ent->fn = kern; ent->dev_mask = 0; }
+    if (ent && dev < 32) ent->dev_mask |= 1u << dev;
+    return cudaSuccess;
+}
+
+// ---- optional phase timing (debug build only: -DGSSD_PHASE_TIMING, see tools/phase_times.py) ----------
+#ifdef GSSD_PHASE_TIMING
+// one array + accessor per translation unit (no relocatable device code in this build)
+#define GSSD_PHASE_DECL(name)                                                                              \
+    namespace gssd { __device__ long long g_phase_clock_##name[32]; }                                      \
+    extern "C" __attribute__((visibility("default"))) int gssd_debug_phase_clocks_##name(long long *out) { \
+        return (int)cudaMemcpyFromSymbol(out, gssd::g_phase_clock_##name, sizeof(long long) * 32);         \
+    }
+#define GSSD_PHASE(name, i, cond)                                                       \
+    do { if ((cond) && threadIdx.x == 0) g_phase_clock_##name[i] = clock64(); } while (0)
+#else
+#define GSSD_PHASE_DECL(name)
+#define GSSD_PHASE(name, i, cond) do { } while (0)
+#endif
+
 // ---- order-preserving float <-> uint32 (larger float <=> larger unsigned) -----------------------
 __device__ __forceinline__ uint32_t f2ord(float f) {
     uint32_t u = __float_as_uint(f);

@@ -11,6 +11,8 @@
 // (detection_pytorch_ver_1point5.py:56, 82-84).
 #include "select.cuh"
 
+GSSD_PHASE_DECL(detect)
+
 namespace gssd {
 
 constexpr int DET_NT = 512;
@@ -36,7 +38,56 @@ struct DetShared {
     uint32_t keep_bits[GSSD_MAX_TOP_K / 32];
 };
 
-// dynamic smem:  [ u32 keys[n] | (aliased later) u32 mask[top_k][words] ]  u64 ckey[k2]  float4 box[top_k]  float area[top_k]
+constexpr int DET_CAND_CAP = 1024;      // candidates that are sorted directly, without a select pass
+
+// ---- block-wide bitonic sort, descending, n2 = power of two >= 64 ------------------------------------------
+// Strides >= 64 go through shared memory with a block barrier; everything below runs inside one warp on a
+// 64-element block held in registers (2 per lane) with shuffles, so a 256-sort needs 4 block barriers
+// instead of 36.
+// sub-stages of phase `sz` that stay inside a 64-element block: stride 32 (the lane's own pair, only when
+// sz >= 64) and strides 16..1 (partner lane = lane ^ stride).  e0 / e1 = global indices of v0 / v1.
+__device__ __forceinline__ void warp_substages(unsigned long long &v0, unsigned long long &v1, int e0, int e1,
+                                               int sz, int lane) {
+    const bool d0 = (e0 & sz) == 0, d1 = (e1 & sz) == 0;             // descending sub-sequence?
+    if (sz >= 64 && (v0 < v1) == d0) { const unsigned long long t = v0; v0 = v1; v1 = t; }
+#pragma unroll
+    for (int st = 16; st >= 1; st >>= 1) {
+        if (st < sz) {
+            const bool lower = (lane & st) == 0;
+            cmpx(v0, shfl_xor_u64(v0, st), d0 == lower);
+            cmpx(v1, shfl_xor_u64(v1, st), d1 == lower);
+        }
+    }
+}
+
+template <int NT>
+__device__ void bitonic_sort_desc(unsigned long long *a, int n2) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_blocks = n2 >> 6;
+    for (int size = 64; size <= n2; size <<= 1) {
+        for (int stride = size >> 1; stride >= 64; stride >>= 1) {      // only for size >= 128
+            for (int i = tid; i < (n2 >> 1); i += NT) {
+                const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const unsigned long long x = a[lo], y = a[hi];
+                if ((x < y) == desc) { a[lo] = y; a[hi] = x; }
+            }
+            __syncthreads();
+        }
+        for (int blk = warp; blk < n_blocks; blk += NT / 32) {
+            const int e0 = (blk << 6) + lane, e1 = e0 + 32;
+            unsigned long long v0 = a[e0], v1 = a[e1];
+            if (size == 64) {                                            // phases 2..32 live in the block too
+                for (int sz = 2; sz < 64; sz <<= 1) warp_substages(v0, v1, e0, e1, sz, lane);
+            }
+            warp_substages(v0, v1, e0, e1, size, lane);
+            a[e0] = v0; a[e1] = v1;
+        }
+        __syncthreads();
+    }
+}
+
+// dynamic smem:  [ u32 keys[n] | (aliased later) u32 mask[top_k][words] ]  u64 ckey[max(k2, CAP)]  float4 box[top_k]  float area[top_k]
 template <bool NMS_MODE>
 __global__ void __launch_bounds__(DET_NT) detect_kernel(DetArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -45,13 +96,14 @@ __global__ void __launch_bounds__(DET_NT) detect_kernel(DetArgs a) {
     const int cl = NMS_MODE ? 0 : blockIdx.x;
     const int b = NMS_MODE ? 0 : blockIdx.y;
     const int n = a.P;                           // number of scores scanned
-    const int top_k = a.top_k, k2 = a.k2;
+    const int top_k = a.top_k;
+    const int cap = max(a.k2, DET_CAND_CAP);
 
     const size_t region_a = max((size_t)n * 4, (size_t)top_k * ((top_k + 31) / 32) * 4);
     uint32_t *keys = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *mask = reinterpret_cast<uint32_t *>(smem_raw);
     unsigned long long *ckey = reinterpret_cast<unsigned long long *>(smem_raw + ((region_a + 15) & ~(size_t)15));
-    float4 *sbox = reinterpret_cast<float4 *>(ckey + k2);
+    float4 *sbox = reinterpret_cast<float4 *>(ckey + cap);
     float *sarea = reinterpret_cast<float *>(sbox + top_k);
 
     float *out_slab = NMS_MODE ? nullptr : a.out + ((size_t)b * a.C + cl) * top_k * 5;
@@ -64,54 +116,67 @@ __global__ void __launch_bounds__(DET_NT) detect_kernel(DetArgs a) {
         return;
     }
 
-    // ---- 1. threshold -> keys ------------------------------------------------------------------------
+    const bool dbg = blockIdx.x == 1 && blockIdx.y == 0;
+    GSSD_PHASE(detect, 0, dbg);
+    // ---- 1. threshold -> keys, and an optimistic compaction of the candidates -----------------------------
     if (tid == 0) { sh.n_cand = 0; sh.n_sel = 0; }
     __syncthreads();
-    int mine = 0;
-    for (int p = tid; p < n; p += DET_NT) {
-        float s;
-        bool cand;
-        if (NMS_MODE) { s = a.scores[p]; cand = true; }
-        else { s = a.conf[((size_t)b * a.P + p) * a.C + cl]; cand = s > a.conf_thresh; }   // strict >, line 69
-        keys[p] = cand ? f2ord(s) : 0u;
-        mine += cand;
+    {
+        const float *src = NMS_MODE ? a.scores : a.conf + (size_t)b * a.P * a.C + cl;
+        const int stride = NMS_MODE ? 1 : a.C;
+        constexpr int U = 4;
+        for (int base = 0; base < n; base += DET_NT * U) {
+            float sv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int p = base + u * DET_NT + tid;
+                sv[u] = p < n ? __ldg(src + (size_t)p * stride) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int p = base + u * DET_NT + tid;
+                const bool cand = p < n && (NMS_MODE || sv[u] > a.conf_thresh);      // strict >, line 69
+                const uint32_t key = cand ? f2ord(sv[u]) : 0u;
+                if (p < n) keys[p] = key;
+                const unsigned m = __ballot_sync(FULL, cand);
+                if (m) {
+                    int slot = 0;
+                    if (lane == 0) slot = atomicAdd(&sh.n_cand, __popc(m));
+                    slot = __shfl_sync(FULL, slot, 0) + __popc(m & ((1u << lane) - 1));
+                    if (cand && slot < DET_CAND_CAP) ckey[slot] = ((unsigned long long)key << 32) | (unsigned)p;
+                }
+            }
+        }
     }
-    mine = warp_sum(mine);
-    if (lane == 0 && mine) atomicAdd(&sh.n_cand, mine);
     __syncthreads();
     const int n_cand = sh.n_cand;
     const int k = min(n_cand, top_k);
     const int words = (k + 31) / 32;             // 32-candidate blocks actually in use
 
+    GSSD_PHASE(detect, 1, dbg);
     if (k > 0) {
-        // ---- 2. top-k candidates (box_utils.py:194-196) ---------------------------------------------
-        SelectResult sel;
-        sel.v = 1u; sel.need = 0; sel.eq = 0; sel.tie_cut = 0; sel.low_first = false;   // key >= 1: every candidate
-        if (n_cand > top_k) sel = radix_select<DET_NT, false>(keys, n, (uint32_t)top_k, false, &sh.sel);
-        for (int i = tid; i < k2; i += DET_NT) ckey[i] = 0ull;
-        __syncthreads();
-        for (int p = tid; p < n; p += DET_NT) {
-            uint32_t key = keys[p];
-            if (key != 0u && sel.selected(key, p)) {
-                int slot = atomicAdd(&sh.n_sel, 1);
-                ckey[slot] = ((unsigned long long)key << 32) | (unsigned)p;
+        // ---- 2. the top_k candidates in descending (score, index) order (box_utils.py:194-196) ---------
+        int n2;
+        if (n_cand <= DET_CAND_CAP) {            // few candidates: sort them all
+            n2 = 64; while (n2 < n_cand) n2 <<= 1;
+            for (int i = n_cand + tid; i < n2; i += DET_NT) ckey[i] = 0ull;
+        } else {                                 // many: radix select of the top_k, then sort those
+            const unsigned long long cut = radix_select<DET_NT, false>(keys, n, 0u, (uint32_t)top_k, false, &sh.sel);
+            n2 = max(a.k2, 64);
+            for (int i = tid; i < n2; i += DET_NT) ckey[i] = 0ull;
+            __syncthreads();
+            for (int p = tid; p < n; p += DET_NT) {
+                const uint32_t key = keys[p];
+                const unsigned long long ck = ((unsigned long long)key << 32) | (unsigned)p;
+                if (key != 0u && ck >= cut) ckey[atomicAdd(&sh.n_sel, 1)] = ck;
             }
         }
         __syncthreads();
-        // ---- 3. bitonic sort, descending (score, index) -------------------------------------------------
-        for (int size = 2; size <= k2; size <<= 1) {
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int i = tid; i < k2 / 2; i += DET_NT) {
-                    int lo = 2 * i - (i & (stride - 1));
-                    int hi = lo + stride;
-                    bool desc = (lo & size) == 0;
-                    unsigned long long x = ckey[lo], y = ckey[hi];
-                    if ((x < y) == desc) { ckey[lo] = y; ckey[hi] = x; }
-                }
-                __syncthreads();
-            }
-        }
-        // ---- 4. boxes of the candidates ------------------------------------------------------------------
+        GSSD_PHASE(detect, 2, dbg);
+        GSSD_PHASE(detect, 3, dbg);
+        bitonic_sort_desc<DET_NT>(ckey, n2);
+        GSSD_PHASE(detect, 4, dbg);
+        // ---- 3. boxes of the candidates ------------------------------------------------------------------
         for (int i = tid; i < k; i += DET_NT) {
             unsigned p = (unsigned)(ckey[i] & 0xffffffffu);
             float4 bx = NMS_MODE ? a.boxes[p]
@@ -120,55 +185,67 @@ __global__ void __launch_bounds__(DET_NT) detect_kernel(DetArgs a) {
             sarea[i] = box_area(bx);                               // box_utils.py:193
         }
         __syncthreads();                                            // keys[] is dead from here: mask aliases it
-        // ---- 5. suppression bitmask: bit j of row i (j > i) = box j is removed when i is kept ------------
-        for (int item = tid; item < k * words; item += DET_NT) {
+        GSSD_PHASE(detect, 5, dbg);
+        // ---- 4. suppression bitmask: bit j of row i (j > i) = box j is removed when i is kept ------------
+        // one warp per (row, 32-column word), one IoU per lane, the word is the ballot
+        const float thr = a.nms_thresh;
+        const float eps = thr * 9.5367431640625e-07f;               // 2^-20 relative: >> the 2-ulp error of the fast divide
+        for (int item = warp; item < k * words; item += DET_NT / 32) {
             const int i = item / words, w = item - i * words;
-            uint32_t bits = 0;
-            if (32 * w + 31 > i) {
-                const float4 bi = sbox[i];
-                const float ai = sarea[i];
-                const int j0 = max(32 * w, i + 1), j1 = min(32 * w + 32, k);
-                for (int j = j0; j < j1; ++j) {
-                    const float4 bj = sbox[j];
-                    float xx1 = fmaxf(bj.x, bi.x), yy1 = fmaxf(bj.y, bi.y);          // box_utils.py:220-223
-                    float xx2 = fminf(bj.z, bi.z), yy2 = fminf(bj.w, bi.w);
-                    float ww = __fsub_rn(xx2, xx1), hh = __fsub_rn(yy2, yy1);
-                    ww = ww < 0.f ? 0.f : ww; hh = hh < 0.f ? 0.f : hh;              // 229-230
-                    float inter = __fmul_rn(ww, hh);
-                    float uni = __fadd_rn(__fsub_rn(sarea[j], inter), ai);           // 233-234
-                    float iou = __fdiv_rn(inter, uni);
-                    if (!(iou <= a.nms_thresh)) bits |= 1u << (j - 32 * w);          // 237 (NaN -> removed)
-                }
+            if (w < (i >> 5)) continue;                             // strictly-lower words are never read
+            const int j = 32 * w + lane;
+            bool sup = false;
+            if (j > i && j < k) {
+                const float4 bi = sbox[i], bj = sbox[j];
+                float xx1 = fmaxf(bj.x, bi.x), yy1 = fmaxf(bj.y, bi.y);              // box_utils.py:220-223
+                float xx2 = fminf(bj.z, bi.z), yy2 = fminf(bj.w, bi.w);
+                float ww = __fsub_rn(xx2, xx1), hh = __fsub_rn(yy2, yy1);
+                ww = ww < 0.f ? 0.f : ww; hh = hh < 0.f ? 0.f : hh;                  // 229-230
+                const float inter = __fmul_rn(ww, hh);
+                const float uni = __fadd_rn(__fsub_rn(sarea[j], inter), sarea[i]);   // 233-234
+                // IoU = inter/uni (IEEE) and "kept iff IoU <= thr" (235-237, NaN -> removed).  The fast divide
+                // decides every case that is not within 2^-20 of the threshold; the rest takes the exact one.
+                const float q = __fdividef(inter, uni);
+                if (uni > 0.f && uni < 1e30f && q > thr + eps) sup = true;
+                else if (uni > 0.f && uni < 1e30f && q < thr - eps) sup = false;
+                else sup = !(__fdiv_rn(inter, uni) <= thr);
             }
-            mask[i * words + w] = bits;
+            const unsigned bits = __ballot_sync(FULL, sup);
+            if (lane == 0) mask[i * words + w] = bits;
         }
         __syncthreads();
-        // ---- 6. greedy resolve by one warp: lane w owns removed-word w --------------------------------------
+        GSSD_PHASE(detect, 6, dbg);
+        // ---- 5. greedy resolve by one warp: lane w owns removed-word w --------------------------------------
         if (warp == 0) {
             uint32_t removed = 0;                                   // word `lane` of the removed set
             for (int c = 0; c < words; ++c) {
                 const int row = 32 * c + lane;
-                uint32_t diag = row < k ? mask[row * words + c] : 0u;
+                const uint32_t diag = row < k ? mask[row * words + c] : 0u;
                 uint32_t cur = __shfl_sync(FULL, removed, c);
                 if (32 * c + 32 > k) cur |= ~0u << (k - 32 * c);    // rows beyond k do not exist
-#pragma unroll
-                for (int t = 0; t < 32; ++t) {
-                    uint32_t d = __shfl_sync(FULL, diag, t);
-                    if (!((cur >> t) & 1u)) cur |= d;
+                // only rows that suppress something inside this block can change `cur`
+                const uint32_t nz = __ballot_sync(FULL, diag != 0u);
+                uint32_t todo = nz & ~cur;
+                while (todo) {                                      // warp-uniform
+                    const int t = __ffs(todo) - 1;
+                    cur |= __shfl_sync(FULL, diag, t);
+                    todo = nz & ~cur & ~((2u << t) - 1u);
                 }
                 const uint32_t kept = ~cur;
                 if (lane == 0) sh.keep_bits[c] = kept;
-                if (lane > c && lane < words) {
-                    uint32_t acc = 0;
-                    for (uint32_t m = kept; m; m &= m - 1) acc |= mask[(32 * c + __ffs(m) - 1) * words + lane];
-                    removed |= acc;
+                // rows kept in this block remove boxes of the later blocks: OR-reduce their words
+                const bool mine_kept = (kept >> lane) & 1u;
+                for (int w = c + 1; w < words; ++w) {
+                    const uint32_t r = __reduce_or_sync(FULL, mine_kept ? mask[row * words + w] : 0u);
+                    if (lane == w) removed |= r;
                 }
             }
         }
         __syncthreads();
     }
 
-    // ---- 7. emit ---------------------------------------------------------------------------------------------
+    GSSD_PHASE(detect, 7, dbg);
+    // ---- 6. emit ---------------------------------------------------------------------------------------------
     int n_keep = 0;
     if (k > 0) for (int c = 0; c < words; ++c) n_keep += __popc(sh.keep_bits[c]);
     if (NMS_MODE) {
@@ -197,6 +274,8 @@ __global__ void __launch_bounds__(DET_NT) detect_kernel(DetArgs a) {
             if (idx_slab) idx_slab[r] = (int32_t)p;
         }
     }
+    __syncthreads();
+    GSSD_PHASE(detect, 8, dbg);
 }
 
 static size_t det_smem_bytes(int n, int top_k, int k2) {
@@ -205,7 +284,8 @@ static size_t det_smem_bytes(int n, int top_k, int k2) {
     size_t m = (size_t)top_k * words * 4;
     if (m > region_a) region_a = m;
     region_a = (region_a + 15) & ~(size_t)15;
-    return region_a + (size_t)k2 * 8 + (size_t)top_k * 16 + (size_t)top_k * 4 + 16;
+    const size_t cap = k2 > DET_CAND_CAP ? k2 : DET_CAND_CAP;
+    return region_a + cap * 8 + (size_t)top_k * 16 + (size_t)top_k * 4 + 16;
 }
 
 static int next_pow2(int v) { int p = 2; while (p < v) p <<= 1; return p; }
@@ -216,8 +296,7 @@ static int launch_detect(DetArgs &a, dim3 grid, cudaStream_t st) {
     size_t smem = det_smem_bytes(a.P, a.top_k, a.k2);
     if (smem > 227 * 1024) return GSSD_ERR_LIMIT;
     auto kern = detect_kernel<NMS_MODE>;
-    if (smem > 48 * 1024)
-        GSSD_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GSSD_RETURN_IF_CUDA(allow_max_smem(reinterpret_cast<const void *>(kern)));
     kern<<<grid, DET_NT, smem, st>>>(a);
     GSSD_AFTER_LAUNCH();
     return GSSD_OK;

@@ -14,6 +14,8 @@
 //            by N (multibox_loss.py:117-119).
 #include "select.cuh"
 
+GSSD_PHASE_DECL(loss)
+
 namespace gssd {
 
 constexpr int LOSS_NT = 256;
@@ -76,91 +78,115 @@ __global__ void __launch_bounds__(LOSS_NT) loss_kernel(LossArgs a) {
     const int p1 = min(a.P, p0 + a.slice);
     const int n_local = max(p1 - p0, 0);
     double acc_l = 0.0, acc_c = 0.0;
+    const bool dbg = blockIdx.x == 0 && blockIdx.y == 0;
+    GSSD_PHASE(loss, 0, dbg);
 
     // ---- sweep 1 ---------------------------------------------------------------------------------
-    for (int p = p0 + tid; p < p1; p += LOSS_NT) {
-        const size_t o = (size_t)b * a.P + p;
-        const uint16_t tag = a.tags[o];
-        const bool pos = tag & 0x8000;
-        const float *row = a.conf + o * C;
-        float key;
-        if (C2) {
-            float2 x = *reinterpret_cast<const float2 *>(row);
-            float s = __fadd_rn(expf(__fsub_rn(x.x, x_max)), expf(__fsub_rn(x.y, x_max)));
-            key = __fsub_rn(__fadd_rn(logf(s), x_max), x.x);
-        } else {
-            float s = 0.f;
-            for (int c = 0; c < C; ++c) s = __fadd_rn(s, expf(__fsub_rn(row[c], x_max)));
-            key = __fsub_rn(__fadd_rn(logf(s), x_max), row[0]);
+    // U priors per thread per trip, loads first: tag (2 B) + conf row; every prior gets zeroed gradients
+    // here, the few selected ones are overwritten in sweep 2 by the same thread.
+    uint32_t *posbits = keys + ((a.slice + 3) & ~3);             // one bit per local prior
+    for (int i = tid; i < (n_local + 31) / 32; i += LOSS_NT) posbits[i] = 0;
+    __syncthreads();
+    constexpr int U = 4;
+    for (int base = p0; base < p1; base += LOSS_NT * U) {
+        uint16_t tg[U];
+        float2 x2[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = base + u * LOSS_NT + tid;
+            const size_t o = (size_t)b * a.P + min(p, p1 - 1);
+            tg[u] = a.tags[o];
+            if (C2) x2[u] = *reinterpret_cast<const float2 *>(a.conf + o * 2);
         }
-        key = pos ? 0.f : __fadd_rn(key, 0.f);               // loss_c[pos] = 0 ; -0 -> +0
-        keys[p - p0] = f2ord(key);
-        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pos) {
-            const float *t = sgt + 5 * (tag & 0x7fff);
-            float4 lt = encode_box(make_float4(t[0], t[1], t[2], t[3]), a.priors[p], a.var0, a.var1);
-            float4 l = a.loc[o];
-            float l0 = smooth_l1(__fsub_rn(l.x, lt.x), g4.x), l1 = smooth_l1(__fsub_rn(l.y, lt.y), g4.y);
-            float l2 = smooth_l1(__fsub_rn(l.z, lt.z), g4.z), l3 = smooth_l1(__fsub_rn(l.w, lt.w), g4.w);
-            acc_l += (double)l0 + (double)l1 + (double)l2 + (double)l3;
-            g4.x = __fdiv_rn(g4.x, n_f); g4.y = __fdiv_rn(g4.y, n_f); g4.z = __fdiv_rn(g4.z, n_f); g4.w = __fdiv_rn(g4.w, n_f);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = base + u * LOSS_NT + tid;
+            const bool ok = p < p1;
+            const size_t o = (size_t)b * a.P + min(p, p1 - 1);
+            const uint16_t tag = tg[u];
+            const bool pos = ok && (tag & 0x8000);
+            float key;
+            if (C2) {
+                const float2 x = x2[u];
+                const float s = __fadd_rn(expf(__fsub_rn(x.x, x_max)), expf(__fsub_rn(x.y, x_max)));
+                key = __fsub_rn(__fadd_rn(logf(s), x_max), x.x);
+            } else {
+                const float *row = a.conf + o * C;
+                float s = 0.f;
+                for (int c = 0; c < C; ++c) s = __fadd_rn(s, expf(__fsub_rn(row[c], x_max)));
+                key = __fsub_rn(__fadd_rn(logf(s), x_max), row[0]);
+            }
+            key = pos ? 0.f : __fadd_rn(key, 0.f);               // loss_c[pos] = 0 ; -0 -> +0
+            const unsigned pm = __ballot_sync(FULL, pos);
+            if (ok) keys[p - p0] = f2ord(key);
+            if (pm && lane == 0) posbits[(p - p0) >> 5] = pm;    // p - p0 is a multiple of 32 for lane 0
+            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pos) {
+                const float *t = sgt + 5 * (tag & 0x7fff);
+                const float4 lt = encode_box(make_float4(t[0], t[1], t[2], t[3]), a.priors[p], a.var0, a.var1);
+                const float4 l = a.loc[o];
+                const float l0 = smooth_l1(__fsub_rn(l.x, lt.x), g4.x), l1 = smooth_l1(__fsub_rn(l.y, lt.y), g4.y);
+                const float l2 = smooth_l1(__fsub_rn(l.z, lt.z), g4.z), l3 = smooth_l1(__fsub_rn(l.w, lt.w), g4.w);
+                acc_l += (double)l0 + (double)l1 + (double)l2 + (double)l3;
+                g4.x = __fdiv_rn(g4.x, n_f); g4.y = __fdiv_rn(g4.y, n_f); g4.z = __fdiv_rn(g4.z, n_f); g4.w = __fdiv_rn(g4.w, n_f);
+            }
+            if (GRADS && ok) {
+                __stcs(&a.grad_loc[o], g4);
+                if (C2) __stcs(reinterpret_cast<float2 *>(a.grad_conf + o * 2), make_float2(0.f, 0.f));
+                else for (int c = 0; c < C; ++c) a.grad_conf[o * C + c] = 0.f;
+            }
         }
-        if (GRADS) __stcs(&a.grad_loc[o], g4);
     }
     __syncthreads();
+    GSSD_PHASE(loss, 1, dbg);
 
     // ---- hard-negative selection (multibox_loss.py:102-106) -----------------------------------------
     long long k = (long long)a.ratio * num_pos;
     if (k > a.P - 1) k = a.P - 1;
-    SelectResult sel;
-    sel.v = 0xffffffffu; sel.need = 0; sel.eq = 0; sel.tie_cut = 0; sel.low_first = true;   // selects nothing
     const bool have_sel = k > 0;
-    if (have_sel) sel = radix_select<LOSS_NT, CLUSTER>(keys, n_local, (uint32_t)k, true, &sel_s);
+    unsigned long long cut = ~0ull;
+    if (have_sel) cut = radix_select<LOSS_NT, CLUSTER>(keys, n_local, (uint32_t)p0, (uint32_t)k, true, &sel_s);
 
-    // ---- sweep 2 ---------------------------------------------------------------------------------
+    GSSD_PHASE(loss, 2, dbg);
+    // ---- sweep 2: only pos | neg priors do any work -----------------------------------------------------
     for (int p = p0 + tid; p < p1; p += LOSS_NT) {
         const size_t o = (size_t)b * a.P + p;
-        const uint16_t tag = a.tags[o];
-        const bool pos = tag & 0x8000;
-        const uint32_t kk = keys[p - p0];
-        const bool neg = have_sel && sel.selected(kk, p - p0);
+        const int li = p - p0;
+        const bool pos = (posbits[li >> 5] >> (li & 31)) & 1u;
+        const bool neg = have_sel && sel_composite(keys[li], (uint32_t)p, true) >= cut;
         if (a.pos_mask) a.pos_mask[o] = pos;
         if (a.neg_mask) a.neg_mask[o] = neg;
+        if (!(pos || neg)) continue;
         const float *row = a.conf + o * C;
-        const bool on = pos || neg;
+        const int t = pos ? (int)__fadd_rn(sgt[5 * (a.tags[o] & 0x7fff) + 4], 1.f) : 0;
         if (C2) {
-            float2 gz = make_float2(0.f, 0.f);
-            if (on) {
-                float2 x = *reinterpret_cast<const float2 *>(row);
-                int t = pos ? (int)__fadd_rn(sgt[5 * (tag & 0x7fff) + 4], 1.f) : 0;
-                float m = fmaxf(x.x, x.y);
-                float e0 = expf(__fsub_rn(x.x, m)), e1 = expf(__fsub_rn(x.y, m));
-                float ls = logf(__fadd_rn(e0, e1));
-                float xt = t == 0 ? x.x : x.y;
-                acc_c += (double)(-(__fsub_rn(__fsub_rn(xt, m), ls)));
+            const float2 x = *reinterpret_cast<const float2 *>(row);
+            const float m = fmaxf(x.x, x.y);
+            const float e0 = expf(__fsub_rn(x.x, m)), e1 = expf(__fsub_rn(x.y, m));
+            const float ls = logf(__fadd_rn(e0, e1));
+            const float xt = t == 0 ? x.x : x.y;
+            acc_c += (double)(-(__fsub_rn(__fsub_rn(xt, m), ls)));
+            if (GRADS) {
+                float2 gz;
                 gz.x = __fdiv_rn(expf(__fsub_rn(__fsub_rn(x.x, m), ls)) - (t == 0 ? 1.f : 0.f), n_f);
                 gz.y = __fdiv_rn(expf(__fsub_rn(__fsub_rn(x.y, m), ls)) - (t == 1 ? 1.f : 0.f), n_f);
+                __stcs(reinterpret_cast<float2 *>(a.grad_conf + o * 2), gz);
             }
-            if (GRADS) __stcs(reinterpret_cast<float2 *>(a.grad_conf + o * 2), gz);
         } else {
-            if (on) {
-                int t = pos ? (int)__fadd_rn(sgt[5 * (tag & 0x7fff) + 4], 1.f) : 0;
-                float m = row[0];
-                for (int c = 1; c < C; ++c) m = fmaxf(m, row[c]);
-                float s = 0.f;
-                for (int c = 0; c < C; ++c) s = __fadd_rn(s, expf(__fsub_rn(row[c], m)));
-                float ls = logf(s);
-                float xt = (t >= 0 && t < C) ? row[t] : row[0];
-                acc_c += (double)(-(__fsub_rn(__fsub_rn(xt, m), ls)));
-                if (GRADS)
-                    for (int c = 0; c < C; ++c)
-                        a.grad_conf[o * C + c] = __fdiv_rn(expf(__fsub_rn(__fsub_rn(row[c], m), ls)) - (c == t ? 1.f : 0.f), n_f);
-            } else if (GRADS) {
-                for (int c = 0; c < C; ++c) a.grad_conf[o * C + c] = 0.f;
-            }
+            float m = row[0];
+            for (int c = 1; c < C; ++c) m = fmaxf(m, row[c]);
+            float s = 0.f;
+            for (int c = 0; c < C; ++c) s = __fadd_rn(s, expf(__fsub_rn(row[c], m)));
+            const float ls = logf(s);
+            const float xt = (t >= 0 && t < C) ? row[t] : row[0];
+            acc_c += (double)(-(__fsub_rn(__fsub_rn(xt, m), ls)));
+            if (GRADS)
+                for (int c = 0; c < C; ++c)
+                    a.grad_conf[o * C + c] = __fdiv_rn(expf(__fsub_rn(__fsub_rn(row[c], m), ls)) - (c == t ? 1.f : 0.f), n_f);
         }
     }
 
+    GSSD_PHASE(loss, 3, dbg);
     // ---- finish ----------------------------------------------------------------------------------
     acc_l = warp_sum(acc_l); acc_c = warp_sum(acc_c);
     if (lane == 0) { s_red[0][warp] = acc_l; s_red[1][warp] = acc_c; }
@@ -193,6 +219,7 @@ __global__ void __launch_bounds__(LOSS_NT) loss_kernel(LossArgs a) {
             a.stats[2] = 0;
         }
     }
+    GSSD_PHASE(loss, 4, dbg);
 }
 
 int pick_cluster_loss(int B, int P) {
@@ -202,15 +229,14 @@ int pick_cluster_loss(int B, int P) {
 }
 
 static size_t loss_smem_bytes(int g_max, int slice) {
-    return (size_t)((g_max + 3) & ~3) * 5 * 4 + (size_t)slice * 4 + 16;
+    return (size_t)((g_max + 3) & ~3) * 5 * 4 + (size_t)((slice + 3) & ~3) * 4 + (size_t)((slice + 31) / 32) * 4 + 32;
 }
 
 template <bool C2, bool CL, bool GR>
 static int launch_loss(LossArgs &a, int S, int g_max, cudaStream_t stream) {
     auto kern = loss_kernel<C2, CL, GR>;
     size_t smem = loss_smem_bytes(g_max, a.slice);
-    if (smem > 48 * 1024)
-        GSSD_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GSSD_RETURN_IF_CUDA(allow_max_smem(reinterpret_cast<const void *>(kern)));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(S, a.B, 1);
     cfg.blockDim = dim3(LOSS_NT, 1, 1);

@@ -11,6 +11,8 @@
 // materialised loc_t / conf_t.
 #include "common.cuh"
 
+GSSD_PHASE_DECL(match)
+
 namespace gssd {
 
 constexpr int MATCH_NT = 256;
@@ -29,12 +31,16 @@ struct MatchArgs {
 
 // dynamic shared memory layout
 //   u64    sbest[G]   packed (IoU bits, ~prior) best prior per GT, this CTA's slice
-//   float  sgt[G][6]  (x1,y1,x2,y2,area,label)
+//   float4 sgt4[G]    GT boxes
+//   float  sarea[G], slabel[G]
 //   int    sbp[G]     best prior per GT over the whole image
+//   int    glist[G]   GT rows that can overlap this CTA's prior slice (ascending)
 //   u16    stag[slice]
 static size_t match_smem_bytes(int g_max, int slice) {
-    return (size_t)g_max * (8 + 6 * 4 + 4) + (size_t)slice * 2 + 16;
+    return (size_t)g_max * (8 + 16 + 4 + 4 + 4 + 4) + (size_t)slice * 2 + 32;
 }
+
+constexpr int MATCH_CULL_MIN_G = 8;       // below this the bounding-box pre-pass costs more than it saves
 
 template <bool MATERIALISE, bool CONF_MAX>
 __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
@@ -43,66 +49,119 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
     const unsigned nranks = cluster.num_blocks();
     const unsigned rank = cluster.block_rank();
     const int b = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g0 = a.gt_off[b];
     const int G = a.gt_off[b + 1] - g0;
 
-    unsigned long long *sbest = reinterpret_cast<unsigned long long *>(smem_raw);     // 8-byte aligned first
-    float *sgt = reinterpret_cast<float *>(sbest + G);
-    int *sbp = reinterpret_cast<int *>(sgt + 6 * G);
-    uint16_t *stag = reinterpret_cast<uint16_t *>(sbp + G);
+    unsigned long long *sbest = reinterpret_cast<unsigned long long *>(smem_raw);     // 16-byte aligned first
+    float4 *sgt4 = reinterpret_cast<float4 *>(sbest + ((G + 1) & ~1));
+    float *sarea = reinterpret_cast<float *>(sgt4 + G);
+    float *slabel = sarea + G;
+    int *sbp = reinterpret_cast<int *>(slabel + G);
+    int *glist = sbp + G;
+    uint16_t *stag = reinterpret_cast<uint16_t *>(glist + G);
     __shared__ int s_warp_cnt[MATCH_NT / 32];
     __shared__ float s_warp_max[MATCH_NT / 32];
-
-    for (int g = tid; g < G; g += MATCH_NT) {
-        const float *row = a.gt + 5 * (size_t)(g0 + g);
-        float4 t = make_float4(row[0], row[1], row[2], row[3]);
-        sgt[6 * g + 0] = t.x; sgt[6 * g + 1] = t.y; sgt[6 * g + 2] = t.z; sgt[6 * g + 3] = t.w;
-        sgt[6 * g + 4] = box_area(t);
-        sgt[6 * g + 5] = row[4];
-        sbest[g] = 0ull;
-    }
-    __syncthreads();
+    __shared__ float s_bbox[4][MATCH_NT / 32];
+    __shared__ int s_nlist;
 
     const int p0 = rank * a.slice;
     const int p1 = min(a.P, p0 + a.slice);
-    float cmax = -INFINITY;
 
-    // ---- IoU sweep -----------------------------------------------------------------------------
-    for (int base = p0 + (tid & ~31); base < p1; base += MATCH_NT) {    // warp-uniform trip count
-        const int p = base + lane;
-        const bool valid = p < p1;
-        float4 pr = valid ? a.priors[p] : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 pb = point_form(pr);
-        float area_b = box_area(pb);
-        if (CONF_MAX && valid) {
+    for (int g = tid; g < G; g += MATCH_NT) {
+        const float *row = a.gt + 5 * (size_t)(g0 + g);
+        const float4 t = make_float4(row[0], row[1], row[2], row[3]);
+        sgt4[g] = t;
+        sarea[g] = box_area(t);
+        slabel[g] = row[4];
+        // an all-zero IoU row resolves to prior 0 (torch.max returns the first maximum)
+        sbest[g] = 0x00000000ffffffffull;
+        glist[g] = g;
+    }
+    if (tid == 0) s_nlist = G;
+    __syncthreads();
+
+    // ---- optional: drop the GT boxes that cannot touch this CTA's slice of priors --------------------------
+    if (G >= MATCH_CULL_MIN_G) {
+        float bx1 = INFINITY, by1 = INFINITY, bx2 = -INFINITY, by2 = -INFINITY;
+        for (int p = p0 + tid; p < p1; p += MATCH_NT) {
+            const float4 pb = point_form(a.priors[p]);
+            bx1 = fminf(bx1, pb.x); by1 = fminf(by1, pb.y); bx2 = fmaxf(bx2, pb.z); by2 = fmaxf(by2, pb.w);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            bx1 = fminf(bx1, __shfl_xor_sync(FULL, bx1, o)); by1 = fminf(by1, __shfl_xor_sync(FULL, by1, o));
+            bx2 = fmaxf(bx2, __shfl_xor_sync(FULL, bx2, o)); by2 = fmaxf(by2, __shfl_xor_sync(FULL, by2, o));
+        }
+        if (lane == 0) { s_bbox[0][warp] = bx1; s_bbox[1][warp] = by1; s_bbox[2][warp] = bx2; s_bbox[3][warp] = by2; }
+        __syncthreads();
+        if (warp == 0) {
+            for (int w = 0; w < MATCH_NT / 32; ++w) {
+                bx1 = fminf(bx1, s_bbox[0][w]); by1 = fminf(by1, s_bbox[1][w]);
+                bx2 = fmaxf(bx2, s_bbox[2][w]); by2 = fmaxf(by2, s_bbox[3][w]);
+            }
+            int n = 0;                                           // ordered compaction, 32 GT rows per step
+            for (int gb = 0; gb < G; gb += 32) {
+                const int g = gb + lane;
+                bool hit = false;
+                if (g < G) {
+                    const float4 t = sgt4[g];
+                    hit = fminf(t.z, bx2) > fmaxf(t.x, bx1) && fminf(t.w, by2) > fmaxf(t.y, by1);
+                }
+                const unsigned m = __ballot_sync(FULL, hit);
+                if (hit) glist[n + __popc(m & ((1u << lane) - 1))] = g;
+                n += __popc(m);
+            }
+            if (lane == 0) s_nlist = n;
+        }
+        __syncthreads();
+    }
+    const int n_list = s_nlist;
+
+    float cmax = -INFINITY;
+    const bool dbg = blockIdx.x == 0 && blockIdx.y == 0;
+    GSSD_PHASE(match, 0, dbg);
+
+    // ---- IoU sweep: a disjoint (GT, prior) pair costs two min/max/sub per axis and one test ------------
+    for (int p = p0 + tid; p < p1; p += MATCH_NT) {
+        const float4 pb = point_form(a.priors[p]);
+        const float area_b = box_area(pb);
+        if (CONF_MAX) {
             const float *row = a.conf + ((size_t)b * a.P + p) * a.C;
             if (a.C == 2) {
-                float2 v = *reinterpret_cast<const float2 *>(row);
+                const float2 v = *reinterpret_cast<const float2 *>(row);
                 cmax = fmaxf(cmax, fmaxf(v.x, v.y));
             } else {
                 for (int c = 0; c < a.C; ++c) cmax = fmaxf(cmax, row[c]);
             }
         }
-        float best = -1.f;
+        float best = 0.f;                                        // IoU >= 0: row 0 wins an all-zero column
         int bidx = 0;
-        for (int g = 0; g < G; ++g) {
-            float4 t = make_float4(sgt[6 * g], sgt[6 * g + 1], sgt[6 * g + 2], sgt[6 * g + 3]);
-            float iou = valid ? box_iou_fast(t, sgt[6 * g + 4], pb, area_b) : 0.f;
-            if (iou > best) { best = iou; bidx = g; }            // first max over GT (torch.max dim 0)
-            // best prior for this GT: warp max of the IoU bits (IoU >= +0, so uint order == float order),
-            // lowest lane among the maxima == lowest prior index
-            unsigned bits = __float_as_uint(iou);
-            unsigned m = __reduce_max_sync(FULL, bits);
-            unsigned who = __ballot_sync(FULL, valid && bits == m);
-            if (lane == 0) {
-                unsigned long long key = ((unsigned long long)m << 32) | (0xffffffffu - (unsigned)(base + __ffs(who) - 1));
-                if (key > sbest[g]) atomicMax(&sbest[g], key);
+        for (int q = 0; q < n_list; ++q) {
+            const int g = glist[q];
+            const float4 t = sgt4[g];
+            const float iw = __fsub_rn(fminf(t.z, pb.z), fmaxf(t.x, pb.x));
+            const float ih = __fsub_rn(fminf(t.w, pb.w), fmaxf(t.y, pb.y));
+            if (iw > 0.f && ih > 0.f) {                          // rare: the boxes overlap
+                const float inter = __fmul_rn(iw, ih);
+                const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(sarea[g], area_b), inter));
+                if (iou > best) { best = iou; bidx = g; }        // first max over GT (torch.max dim 0)
+                // best prior of this GT: max of (IoU bits, ~prior) over whichever lanes are here together;
+                // IoU >= +0 so the uint order of the bits is the float order, ~prior breaks ties downwards
+                const unsigned act = __activemask();
+                const unsigned bits = __float_as_uint(iou);
+                const unsigned m = __reduce_max_sync(act, bits);
+                const unsigned who = __ballot_sync(act, bits == m);
+                if (lane == __ffs(who) - 1) {
+                    const unsigned long long key = ((unsigned long long)m << 32) | (0xffffffffu - (unsigned)p);
+                    if (key > sbest[g]) atomicMax(&sbest[g], key);
+                }
             }
         }
-        if (valid) stag[p - p0] = (uint16_t)(bidx | (!(best < a.threshold) ? 0x8000 : 0));   // box_utils.py:108
+        stag[p - p0] = (uint16_t)(bidx | (!(best < a.threshold) ? 0x8000 : 0));   // box_utils.py:108
     }
     __syncthreads();
+    GSSD_PHASE(match, 1, dbg);
 
     // ---- best prior per GT over the whole image, then the sequential force match -------------------
     if (nranks > 1) cluster.sync();
@@ -110,7 +169,7 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
         unsigned long long m = sbest[g];
         for (unsigned r = 0; r < nranks; ++r) {
             if (r == rank) continue;
-            unsigned long long o = cluster.map_shared_rank(sbest, r)[g];
+            const unsigned long long o = cluster.map_shared_rank(sbest, r)[g];
             m = o > m ? o : m;
         }
         sbp[g] = (int)(0xffffffffu - (unsigned)(m & 0xffffffffu));
@@ -118,25 +177,25 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
     __syncthreads();
     if (tid == 0) {
         for (int g = 0; g < G; ++g) {                            // box_utils.py:101-105, in GT order
-            int bp = sbp[g];
+            const int bp = sbp[g];
             if (bp >= p0 && bp < p1) stag[bp - p0] = (uint16_t)(0x8000 | g);
         }
     }
     __syncthreads();
 
+    GSSD_PHASE(match, 2, dbg);
     // ---- emit --------------------------------------------------------------------------------------
     int npos = 0;
     for (int p = p0 + tid; p < p1; p += MATCH_NT) {
-        uint16_t tag = stag[p - p0];
+        const uint16_t tag = stag[p - p0];
         const bool pos = tag & 0x8000;
         const int g = tag & 0x7fff;
         npos += pos;
         const size_t o = (size_t)b * a.P + p;
         if (a.tags) a.tags[o] = tag;
         if (MATERIALISE) {
-            float4 t = make_float4(sgt[6 * g], sgt[6 * g + 1], sgt[6 * g + 2], sgt[6 * g + 3]);
-            a.loc_t[o] = encode_box(t, a.priors[p], a.var0, a.var1);                  // box_utils.py:109-110
-            float c = pos ? __fadd_rn(sgt[6 * g + 5], 1.f) : 0.f;                     // 107-108
+            a.loc_t[o] = encode_box(sgt4[g], a.priors[p], a.var0, a.var1);            // box_utils.py:109-110
+            const float c = pos ? __fadd_rn(slabel[g], 1.f) : 0.f;                    // 107-108
             a.conf_t[o] = (int64_t)c;                                                 // 111
             if (a.bti_out) a.bti_out[o] = g;
         }
@@ -144,7 +203,7 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
     if (a.num_pos || CONF_MAX) {
         npos = warp_sum(npos);
         cmax = warp_max(cmax);
-        if (lane == 0) { s_warp_cnt[tid >> 5] = npos; s_warp_max[tid >> 5] = cmax; }
+        if (lane == 0) { s_warp_cnt[warp] = npos; s_warp_max[warp] = cmax; }
         __syncthreads();
         if (tid == 0) {
             int tot = 0; float mx = -INFINITY;
@@ -156,7 +215,9 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
             }
         }
     }
+    GSSD_PHASE(match, 3, dbg);
     if (nranks > 1) cluster.sync();     // keep sbest alive until every CTA of the image has read it
+    GSSD_PHASE(match, 4, dbg);
 }
 
 static int pick_cluster(int B, int P) {
@@ -173,8 +234,7 @@ static int launch_match(const MatchArgs &a_in, int B, int g_max, cudaStream_t st
     a.slice = ceil_div(a.P, S);
     size_t smem = match_smem_bytes(g_max, a.slice);
     auto kern = match_kernel<MAT, CMAX>;
-    if (smem > 48 * 1024)
-        GSSD_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GSSD_RETURN_IF_CUDA(allow_max_smem(reinterpret_cast<const void *>(kern)));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(S, B, 1);
     cfg.blockDim = dim3(MATCH_NT, 1, 1);

@@ -4,7 +4,12 @@
 // The keys of one image live in shared memory as order-preserving uint32 (f2ord), either in one CTA
 // or split in contiguous slices across the CTAs of a thread-block cluster; histograms are then
 // summed over distributed shared memory.  The result is the exact "k largest keys" set with a
-// deterministic rule for equal keys at the cut (lower index first or higher index first).
+// deterministic rule for equal keys (lower index first or higher index first), expressed as one
+// 64-bit cut: an element is selected iff  composite(key, index) >= cut,  where
+//   composite = key << 32 | (low_first ? ~index : index).
+// MSB-first 8-bit digits; as soon as the bin that holds the k-th key has <= 32 members (typically
+// after two passes) those members are gathered and ranked by one warp instead of running the
+// remaining passes.
 #pragma once
 #include "common.cuh"
 
@@ -15,51 +20,59 @@ struct SelectShared {
     uint32_t total[256];
     uint32_t warp_tmp[32];
     uint32_t digit, k_rem, eq_total, eq_local_before;
-    int      tie_cut;
+    uint32_t fin_count;
+    int      tie_idx;
+    unsigned long long fin_list[32];
+    unsigned long long cut;
 };
 
-struct SelectResult {
-    uint32_t v;        // value of the k-th largest key
-    uint32_t need;     // how many keys equal to v belong to the selection (>= 1)
-    uint32_t eq;       // how many keys equal to v exist (whole image)
-    int      tie_cut;  // local index bound for equal keys, see selected()
-    bool     low_first;
-    __device__ __forceinline__ bool selected(uint32_t key, int local_idx) const {
-        if (key > v) return true;
-        if (key != v) return false;
-        return low_first ? local_idx < tie_cut : local_idx >= tie_cut;
-    }
-};
+__device__ __forceinline__ unsigned long long sel_composite(uint32_t key, uint32_t index, bool low_first) {
+    return ((unsigned long long)key << 32) | (low_first ? ~index : index);
+}
 
-// NT threads per CTA (multiple of 32, >= 256).  keys[0..n_local) are this CTA's slice.  k >= 1 and
-// k <= total number of keys in the image.  CLUSTER: slices are ordered by cluster rank.
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+    unsigned lo = __shfl_xor_sync(FULL, (unsigned)v, m), hi = __shfl_xor_sync(FULL, (unsigned)(v >> 32), m);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// compare-exchange half: keep the larger (keep_max) or the smaller of (mine, other)
+__device__ __forceinline__ void cmpx(unsigned long long &mine, unsigned long long other, bool keep_max) {
+    if ((other > mine) == keep_max) mine = other;
+}
+
+// NT threads per CTA (multiple of 32, >= 256).  keys[0..n_local) are this CTA's slice, whose first
+// element has image-wide index `index_base`.  1 <= k <= number of keys in the image.
+// CLUSTER: slices are ordered by cluster rank.  Returns the cut (may differ between the CTAs of an
+// image, each value classifies that CTA's own elements correctly).
 template <int NT, bool CLUSTER>
-__device__ SelectResult radix_select(const uint32_t *keys, int n_local, uint32_t k, bool low_first,
-                                     SelectShared *s) {
+__device__ unsigned long long radix_select(const uint32_t *keys, int n_local, uint32_t index_base, uint32_t k,
+                                           bool low_first, SelectShared *s) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned nranks = CLUSTER ? cluster.num_blocks() : 1;
     const unsigned rank = CLUSTER ? cluster.block_rank() : 0;
+    const int n_round = (n_local + NT - 1) / NT * NT;
 
-    uint32_t prefix = 0, mask = 0, k_rem = k;
+    if (tid == 0) s->fin_count = 0;
+    uint32_t prefix = 0, mask = 0, k_rem = k, eq_total = 0;
     int buf = 0;
 #pragma unroll 1
     for (int shift = 24; shift >= 0; shift -= 8, buf ^= 1) {
         for (int i = tid; i < 256; i += NT) s->hist[buf][i] = 0;
         __syncthreads();
-        const int n_round = (n_local + NT - 1) / NT * NT;
         for (int i = tid; i < n_round; i += NT) {
             bool in = i < n_local;
-            uint32_t key = in ? keys[i] : 0;
+            const uint32_t key = in ? keys[i] : 0;
             in = in && ((key & mask) == prefix);
-            unsigned act = __ballot_sync(FULL, in);
+            const unsigned act = __ballot_sync(FULL, in);
             if (in) {
-                uint32_t d = (key >> shift) & 255u;
-                unsigned peers = __match_any_sync(act, d);       // one atomic per distinct digit
+                const uint32_t d = (key >> shift) & 255u;
+                const unsigned peers = __match_any_sync(act, d);     // one atomic per distinct digit
                 if (lane == __ffs(peers) - 1) atomicAdd(&s->hist[buf][d], __popc(peers));
             }
         }
         __syncthreads();
+        const uint32_t *tot = s->hist[buf];
         if (CLUSTER) {
             cluster.sync();
             for (int i = tid; i < 256; i += NT) {
@@ -67,26 +80,23 @@ __device__ SelectResult radix_select(const uint32_t *keys, int n_local, uint32_t
                 for (unsigned r = 0; r < nranks; ++r) t += cluster.map_shared_rank(&s->hist[buf][0], r)[i];
                 s->total[i] = t;
             }
-        } else {
-            for (int i = tid; i < 256; i += NT) s->total[i] = s->hist[buf][i];
+            tot = s->total;
+            __syncthreads();
         }
-        __syncthreads();
         // suffix sums over the 256 bins (bin 255 first): the first 8 warps own one bin per thread
         if (tid < 256) {
-            uint32_t c = s->total[tid];
+            const uint32_t c = tot[tid];
             uint32_t incl = c;                                   // inclusive suffix within the warp
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_down_sync(FULL, incl, o);
+                const uint32_t t = __shfl_down_sync(FULL, incl, o);
                 if (lane + o < 32) incl += t;
             }
             if (lane == 0) s->warp_tmp[warp] = incl;             // warp total
-            __syncwarp();
-            // named barrier over the first 256 threads only
-            asm volatile("bar.sync 1, 256;");
+            asm volatile("bar.sync 1, 256;");                    // the first 256 threads only
             uint32_t above = 0;
             for (int w = warp + 1; w < 8; ++w) above += s->warp_tmp[w];
-            uint32_t excl = above + incl - c;                    // keys in bins > tid
+            const uint32_t excl = above + incl - c;              // keys in bins > tid
             if (excl < k_rem && k_rem <= excl + c) {
                 s->digit = tid; s->k_rem = k_rem - excl; s->eq_total = c;
             }
@@ -95,20 +105,52 @@ __device__ SelectResult radix_select(const uint32_t *keys, int n_local, uint32_t
         prefix |= s->digit << shift;
         mask |= 255u << shift;
         k_rem = s->k_rem;
+        eq_total = s->eq_total;
+        if (eq_total <= 32u) break;                              // few enough to rank directly
     }
-    buf ^= 1;   // the buffer of the last pass: hist[buf][digit] = local count of keys == prefix
 
-    SelectResult r;
-    r.v = prefix; r.need = k_rem; r.eq = s->eq_total; r.low_first = low_first;
-    // All ties selected: no index rule needed.
-    if (r.need == r.eq) {
-        r.tie_cut = low_first ? 0x7fffffff : 0;
-        if (CLUSTER) cluster.sync();        // nobody leaves while its histograms may still be read
-        return r;
+    if (eq_total <= 32u) {
+        // ---- gather the members of the bin into rank 0's list and rank them with one warp -------------
+        SelectShared *s0 = CLUSTER ? cluster.map_shared_rank(s, 0) : s;
+        for (int i = tid; i < n_local; i += NT) {
+            const uint32_t key = keys[i];
+            if ((key & mask) == prefix) {
+                const uint32_t slot = atomicAdd(&s0->fin_count, 1u);
+                s0->fin_list[slot] = sel_composite(key, index_base + (uint32_t)i, low_first);
+            }
+        }
+        if (CLUSTER) cluster.sync(); else __syncthreads();
+        if (warp == 0) {
+            unsigned long long c = lane < (int)eq_total ? s0->fin_list[lane] : 0ull;
+#pragma unroll
+            for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+                for (int st = size >> 1; st >= 1; st >>= 1) {
+                    const bool lower = (lane & st) == 0, desc = (lane & size) == 0;
+                    cmpx(c, shfl_xor_u64(c, st), desc == lower);
+                }
+            }
+            c = ((unsigned long long)__shfl_sync(FULL, (unsigned)(c >> 32), k_rem - 1) << 32) |
+                __shfl_sync(FULL, (unsigned)c, k_rem - 1);
+            if (lane == 0) s->cut = c;
+        }
+        __syncthreads();
+        const unsigned long long cut = s->cut;
+        if (CLUSTER) cluster.sync();         // rank 0's list / everybody's histograms stay alive until here
+        return cut;
     }
-    // Partial tie: `need` of the `eq` equal keys, in index order (from the low or the high end).
-    uint32_t eq_local = s->hist[buf][s->digit];
-    uint32_t before = 0;                    // equal keys in slices of lower rank
+
+    // ---- all 32 bits resolved and more than 32 keys are exactly equal to v = prefix -----------------------
+    buf ^= 1;                                // buffer of the last pass: hist[buf][digit] = local count of keys == v
+    const uint32_t v = prefix, need = k_rem;
+    const unsigned long long take_all = (unsigned long long)v << 32;
+    const unsigned long long take_none = ((unsigned long long)v << 32) + 0x100000000ull;
+    if (need == eq_total) {
+        if (CLUSTER) cluster.sync();
+        return take_all;
+    }
+    const uint32_t eq_local = s->hist[buf][s->digit];
+    uint32_t before = 0;                     // equal keys in slices of lower rank
     if (CLUSTER) {
         if (tid == 0) {
             uint32_t t = 0;
@@ -121,33 +163,32 @@ __device__ SelectResult radix_select(const uint32_t *keys, int n_local, uint32_t
     }
     // number of local equal keys to take, counted from the preferred end
     long long want;
-    if (low_first) want = (long long)r.need - before;
-    else           want = (long long)r.need - ((long long)r.eq - before - eq_local);
-    if (want <= 0) { r.tie_cut = low_first ? 0 : 0x7fffffff; return r; }
-    if (want >= (long long)eq_local) { r.tie_cut = low_first ? 0x7fffffff : 0; return r; }
-    // find the local index of the want-th equal key from the preferred end (block scan in index order)
-    if (tid == 0) s->tie_cut = -1;
+    if (low_first) want = (long long)need - before;
+    else           want = (long long)need - ((long long)eq_total - before - eq_local);
+    if (want <= 0) return take_none;
+    if (want >= (long long)eq_local) return take_all;
+    // local index of the want-th equal key from the preferred end (block scan in visiting order)
+    if (tid == 0) s->tie_idx = 0;
     __syncthreads();
     uint32_t running = 0;
     const int n_chunks = (n_local + NT - 1) / NT;
     for (int c = 0; c < n_chunks; ++c) {
-        int chunk = low_first ? c : n_chunks - 1 - c;
-        int i = chunk * NT + (low_first ? tid : NT - 1 - tid);   // thread order = visiting order
-        bool eqk = i < n_local && keys[i] == r.v;
-        unsigned b = __ballot_sync(FULL, eqk);
+        const int chunk = low_first ? c : n_chunks - 1 - c;
+        const int i = chunk * NT + (low_first ? tid : NT - 1 - tid);   // thread order = visiting order
+        const bool eqk = i < n_local && keys[i] == v;
+        const unsigned b = __ballot_sync(FULL, eqk);
         if (lane == 0) s->warp_tmp[warp] = __popc(b);
         __syncthreads();
         uint32_t off = running;
         for (int w = 0; w < warp; ++w) off += s->warp_tmp[w];
-        uint32_t my = off + __popc(b & ((1u << lane) - 1)) + 1; // 1-based position among equal keys
-        if (eqk && my == (uint32_t)want) s->tie_cut = i;
+        const uint32_t my = off + __popc(b & ((1u << lane) - 1)) + 1;  // 1-based position among equal keys
+        if (eqk && my == (uint32_t)want) s->tie_idx = i;
         for (int w = 0; w < NT / 32; ++w) running += s->warp_tmp[w];
         __syncthreads();
-        if (running >= (uint32_t)want) break;                    // uniform: running is block-wide
+        if (running >= (uint32_t)want) break;                          // uniform: running is block-wide
     }
     __syncthreads();
-    r.tie_cut = low_first ? s->tie_cut + 1 : s->tie_cut;          // low: idx < cut ; high: idx >= cut
-    return r;
+    return sel_composite(v, index_base + (uint32_t)s->tie_idx, low_first);
 }
 
 }  // namespace gssd

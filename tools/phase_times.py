@@ -1,0 +1,22 @@
+"""Per-phase clock64 breakdown of one CTA of each kernel (needs the --phase-timing debug build)."""
+import sys, os, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from grouped_ssd_pytorch_b200 import build
+build.LIB = build.LIB.replace(".so", "_dbg.so")
+build.stale = lambda: False
+import torch
+from grouped_ssd_pytorch_b200 import _lib
+lib = _lib.require_cuda()
+import runpy
+for args in (["32", "v2", "5", "2"], ["256", "v2", "5", "2"], ["1024", "v2", "5", "2"], ["64", "v2_512", "32", "2"]):
+    sys.argv = ["ncu_target.py"] + args
+    runpy.run_path(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_target.py"), run_name="__main__")
+    for name, labels in (("match", ["sweep", "reduce+force", "emit", "tail-sync"]),
+                         ("loss", ["sweep1", "select", "sweep2", "finish"]),
+                         ("detect", ["threshold", "select", "collect", "sort", "decode", "mask", "resolve", "emit"])):
+        buf = (ctypes.c_longlong * 32)()
+        getattr(lib, "gssd_debug_phase_clocks_" + name)(buf)
+        t = list(buf)
+        d = [t[i + 1] - t[i] for i in range(len(labels))]
+        print("B=%s %s %-7s total %7d cyc: " % (args[0], args[1], name, t[len(labels)] - t[0]) +
+              "  ".join("%s=%d" % (l, x) for l, x in zip(labels, d)), flush=True)
