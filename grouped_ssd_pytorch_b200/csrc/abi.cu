@@ -6,7 +6,6 @@
 namespace gssd {
 static std::atomic<unsigned long long> g_launches{0};
 void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
-int pick_cluster_loss(int B, int P);
 }  // namespace gssd
 
 extern "C" int gssd_abi_version(void) { return GSSD_ABI_VERSION; }

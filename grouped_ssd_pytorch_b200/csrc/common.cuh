@@ -60,6 +60,33 @@ static inline cudaError_t allow_max_smem(const void *kern) {
     return cudaSuccess;
 }
 
+// Cluster size (CTAs per image, 1/2/4/8) for the per-image kernels: enough CTAs to fill the machine, and a
+// CTA count that packs into whole waves (`slots` = resident CTAs of the kernel on the device), with a fixed
+// cost per CTA (`fixed`, in priors) for staging, cluster barriers and the tail of each phase.
+static inline int pick_cluster_size(int B, int P, int slots, int fixed) {
+    int best_s = 1;
+    double best_cost = 1e300;
+    for (int s = 1; s <= 8; s *= 2) {
+        if (s > 1 && P / s < 512) break;
+        const long ctas = (long)B * s;
+        const long waves = (ctas + slots - 1) / slots;
+        const double cost = (double)waves * ((double)(P + s - 1) / s + fixed + (s > 1 ? fixed : 0));
+        if (cost < best_cost * 0.97) { best_cost = cost; best_s = s; }
+    }
+    return best_s;
+}
+
+static inline int resident_ctas(const void *kern, int threads, size_t smem) {
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) {
+        per_sm = 1;
+        cudaGetLastError();
+    }
+    return sms * per_sm;
+}
+
 // ---- optional phase timing (debug build only: -DGSSD_PHASE_TIMING, see tools/phase_times.py) ----------
 #ifdef GSSD_PHASE_TIMING
 // one array + accessor per translation unit (no relocatable device code in this build)

@@ -15,7 +15,7 @@ GSSD_PHASE_DECL(detect)
 
 namespace gssd {
 
-constexpr int DET_NT = 512;
+constexpr int DET_NT = 1024;
 
 struct DetArgs {
     // Detect mode
@@ -122,28 +122,56 @@ __global__ void __launch_bounds__(DET_NT) detect_kernel(DetArgs a) {
     if (tid == 0) { sh.n_cand = 0; sh.n_sel = 0; }
     __syncthreads();
     {
-        const float *src = NMS_MODE ? a.scores : a.conf + (size_t)b * a.P * a.C + cl;
-        const int stride = NMS_MODE ? 1 : a.C;
-        constexpr int U = 4;
-        for (int base = 0; base < n; base += DET_NT * U) {
-            float sv[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int p = base + u * DET_NT + tid;
-                sv[u] = p < n ? __ldg(src + (size_t)p * stride) : 0.f;
+        // append one candidate per lane: warp-aggregated slot allocation
+        auto push = [&](bool cand, uint32_t key, int p) {
+            const unsigned m = __ballot_sync(FULL, cand);
+            if (m) {
+                int slot = 0;
+                if (lane == 0) slot = atomicAdd(&sh.n_cand, __popc(m));
+                slot = __shfl_sync(FULL, slot, 0) + __popc(m & ((1u << lane) - 1));
+                if (cand && slot < DET_CAND_CAP) ckey[slot] = ((unsigned long long)key << 32) | (unsigned)p;
             }
+        };
+        constexpr int U = 4;
+        if (!NMS_MODE && a.C == 2 && (n & 1) == 0) {
+            // rows are (background, class 1) pairs: one float4 = two priors, the .y / .w lanes are ours
+            const float4 *src = reinterpret_cast<const float4 *>(a.conf + (size_t)b * a.P * 2);
+            const int n4 = n >> 1;
+            for (int base = 0; base < n4; base += DET_NT * U) {
+                float4 sv[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int p = base + u * DET_NT + tid;
-                const bool cand = p < n && (NMS_MODE || sv[u] > a.conf_thresh);      // strict >, line 69
-                const uint32_t key = cand ? f2ord(sv[u]) : 0u;
-                if (p < n) keys[p] = key;
-                const unsigned m = __ballot_sync(FULL, cand);
-                if (m) {
-                    int slot = 0;
-                    if (lane == 0) slot = atomicAdd(&sh.n_cand, __popc(m));
-                    slot = __shfl_sync(FULL, slot, 0) + __popc(m & ((1u << lane) - 1));
-                    if (cand && slot < DET_CAND_CAP) ckey[slot] = ((unsigned long long)key << 32) | (unsigned)p;
+                for (int u = 0; u < U; ++u) {
+                    const int q = base + u * DET_NT + tid;
+                    sv[u] = q < n4 ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int q = base + u * DET_NT + tid;
+                    const bool ok = q < n4;
+                    const bool c0 = ok && sv[u].y > a.conf_thresh, c1 = ok && sv[u].w > a.conf_thresh;   // strict >, line 69
+                    const uint32_t k0 = c0 ? f2ord(sv[u].y) : 0u, k1 = c1 ? f2ord(sv[u].w) : 0u;
+                    if (ok) *reinterpret_cast<uint2 *>(keys + 2 * q) = make_uint2(k0, k1);
+                    push(c0, k0, 2 * q);
+                    push(c1, k1, 2 * q + 1);
+                }
+            }
+        } else {
+            const float *src = NMS_MODE ? a.scores : a.conf + (size_t)b * a.P * a.C + cl;
+            const int stride = NMS_MODE ? 1 : a.C;
+            for (int base = 0; base < n; base += DET_NT * U) {
+                float sv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int p = base + u * DET_NT + tid;
+                    sv[u] = p < n ? __ldg(src + (size_t)p * stride) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int p = base + u * DET_NT + tid;
+                    const bool cand = p < n && (NMS_MODE || sv[u] > a.conf_thresh);  // strict >, line 69
+                    const uint32_t key = cand ? f2ord(sv[u]) : 0u;
+                    if (p < n) keys[p] = key;
+                    push(cand, key, p);
                 }
             }
         }
@@ -190,28 +218,32 @@ __global__ void __launch_bounds__(DET_NT) detect_kernel(DetArgs a) {
         // one warp per (row, 32-column word), one IoU per lane, the word is the ballot
         const float thr = a.nms_thresh;
         const float eps = thr * 9.5367431640625e-07f;               // 2^-20 relative: >> the 2-ulp error of the fast divide
-        for (int item = warp; item < k * words; item += DET_NT / 32) {
-            const int i = item / words, w = item - i * words;
-            if (w < (i >> 5)) continue;                             // strictly-lower words are never read
-            const int j = 32 * w + lane;
-            bool sup = false;
-            if (j > i && j < k) {
-                const float4 bi = sbox[i], bj = sbox[j];
-                float xx1 = fmaxf(bj.x, bi.x), yy1 = fmaxf(bj.y, bi.y);              // box_utils.py:220-223
-                float xx2 = fminf(bj.z, bi.z), yy2 = fminf(bj.w, bi.w);
-                float ww = __fsub_rn(xx2, xx1), hh = __fsub_rn(yy2, yy1);
-                ww = ww < 0.f ? 0.f : ww; hh = hh < 0.f ? 0.f : hh;                  // 229-230
-                const float inter = __fmul_rn(ww, hh);
-                const float uni = __fadd_rn(__fsub_rn(sarea[j], inter), sarea[i]);   // 233-234
-                // IoU = inter/uni (IEEE) and "kept iff IoU <= thr" (235-237, NaN -> removed).  The fast divide
-                // decides every case that is not within 2^-20 of the threshold; the rest takes the exact one.
-                const float q = __fdividef(inter, uni);
-                if (uni > 0.f && uni < 1e30f && q > thr + eps) sup = true;
-                else if (uni > 0.f && uni < 1e30f && q < thr - eps) sup = false;
-                else sup = !(__fdiv_rn(inter, uni) <= thr);
+        for (int i = warp; i < k; i += DET_NT / 32) {
+            const float4 bi = sbox[i];
+            const float ai = sarea[i];
+            for (int w = i >> 5; w < words; ++w) {                  // strictly-lower words are never read
+                const int j = 32 * w + lane;
+                bool sup = false;
+                if (j > i && j < k) {
+                    const float4 bj = sbox[j];
+                    const float xx1 = fmaxf(bj.x, bi.x), yy1 = fmaxf(bj.y, bi.y);    // box_utils.py:220-223
+                    const float xx2 = fminf(bj.z, bi.z), yy2 = fminf(bj.w, bi.w);
+                    float ww = __fsub_rn(xx2, xx1), hh = __fsub_rn(yy2, yy1);
+                    ww = ww < 0.f ? 0.f : ww; hh = hh < 0.f ? 0.f : hh;              // 229-230
+                    const float inter = __fmul_rn(ww, hh);
+                    const float uni = __fadd_rn(__fsub_rn(sarea[j], inter), ai);     // 233-234
+                    // IoU = inter/uni (IEEE) and "kept iff IoU <= thr" (235-237, NaN -> removed).  The fast
+                    // divide decides every case that is not within 2^-20 of the threshold; the rest takes
+                    // the exact one.
+                    const float q = __fdividef(inter, uni);
+                    const bool sane = uni > 0.f && uni < 1e30f;
+                    if (sane && q > thr + eps) sup = true;
+                    else if (sane && q < thr - eps) sup = false;
+                    else sup = !(__fdiv_rn(inter, uni) <= thr);
+                }
+                const unsigned bits = __ballot_sync(FULL, sup);
+                if (lane == 0) mask[i * words + w] = bits;
             }
-            const unsigned bits = __ballot_sync(FULL, sup);
-            if (lane == 0) mask[i * words + w] = bits;
         }
         __syncthreads();
         GSSD_PHASE(detect, 6, dbg);

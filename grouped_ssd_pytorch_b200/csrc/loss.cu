@@ -43,7 +43,7 @@ __device__ __forceinline__ float smooth_l1(float d, float &grad) {
 
 // C2: num_classes == 2 fast path (float2 rows)
 template <bool C2, bool CLUSTER, bool GRADS>
-__global__ void __launch_bounds__(LOSS_NT) loss_kernel(LossArgs a) {
+__global__ void __launch_bounds__(LOSS_NT, 4) loss_kernel(LossArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SelectShared sel_s;
     __shared__ double s_red[2][LOSS_NT / 32];
@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(LOSS_NT) loss_kernel(LossArgs a) {
         for (int u = 0; u < U; ++u) {
             const int p = base + u * LOSS_NT + tid;
             const size_t o = (size_t)b * a.P + min(p, p1 - 1);
-            tg[u] = a.tags[o];
-            if (C2) x2[u] = *reinterpret_cast<const float2 *>(a.conf + o * 2);
+            tg[u] = __ldcs(a.tags + o);
+            if (C2) x2[u] = ldg_stream(reinterpret_cast<const float2 *>(a.conf + o * 2));
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(LOSS_NT) loss_kernel(LossArgs a) {
             if (pos) {
                 const float *t = sgt + 5 * (tag & 0x7fff);
                 const float4 lt = encode_box(make_float4(t[0], t[1], t[2], t[3]), a.priors[p], a.var0, a.var1);
-                const float4 l = a.loc[o];
+                const float4 l = ldg_stream(a.loc + o);
                 const float l0 = smooth_l1(__fsub_rn(l.x, lt.x), g4.x), l1 = smooth_l1(__fsub_rn(l.y, lt.y), g4.y);
                 const float l2 = smooth_l1(__fsub_rn(l.z, lt.z), g4.z), l3 = smooth_l1(__fsub_rn(l.w, lt.w), g4.w);
                 acc_l += (double)l0 + (double)l1 + (double)l2 + (double)l3;
@@ -222,19 +222,19 @@ __global__ void __launch_bounds__(LOSS_NT) loss_kernel(LossArgs a) {
     GSSD_PHASE(loss, 4, dbg);
 }
 
-int pick_cluster_loss(int B, int P) {
-    int s = 1;
-    while (s < 8 && B * s < 296 && P / (s * 2) >= 512) s *= 2;
-    return s;
-}
-
 static size_t loss_smem_bytes(int g_max, int slice) {
     return (size_t)((g_max + 3) & ~3) * 5 * 4 + (size_t)((slice + 3) & ~3) * 4 + (size_t)((slice + 31) / 32) * 4 + 32;
 }
 
-template <bool C2, bool CL, bool GR>
-static int launch_loss(LossArgs &a, int S, int g_max, cudaStream_t stream) {
-    auto kern = loss_kernel<C2, CL, GR>;
+template <bool C2, bool GR>
+static int launch_loss(LossArgs &a, int g_max, cudaStream_t stream) {
+    // the cluster-capable instantiation also runs as a 1-CTA "cluster"; pick the size from its occupancy
+    auto kern_cl = loss_kernel<C2, true, GR>;
+    GSSD_RETURN_IF_CUDA(allow_max_smem(reinterpret_cast<const void *>(kern_cl)));
+    const int slots = resident_ctas(reinterpret_cast<const void *>(kern_cl), LOSS_NT, loss_smem_bytes(g_max, ceil_div(a.P, 4)));
+    const int S = pick_cluster_size(a.B, a.P, slots, 384);
+    a.slice = ceil_div(a.P, S);
+    auto kern = S > 1 ? kern_cl : loss_kernel<C2, false, GR>;
     size_t smem = loss_smem_bytes(g_max, a.slice);
     GSSD_RETURN_IF_CUDA(allow_max_smem(reinterpret_cast<const void *>(kern)));
     cudaLaunchConfig_t cfg = {};
@@ -286,7 +286,6 @@ extern "C" int gssd_mbox_loss(const float *loc, const float *conf, const float *
     if ((grad_loc == nullptr) != (grad_conf == nullptr)) return GSSD_ERR_ARG;
     if (g_max > GSSD_MAX_GT_PER_IMAGE || P > GSSD_MAX_PRIORS) return GSSD_ERR_LIMIT;
     if (global_stats && n_global_stats <= 0) return GSSD_ERR_ARG;
-    const int S = pick_cluster_loss(B, P);
     if (ws_bytes < gssd_workspace_bytes(GSSD_WS_LOSS, B, P, C, sum_G, 0)) return GSSD_ERR_WS;
     LossArgs a = {};
     a.loc = reinterpret_cast<const float4 *>(loc); a.conf = conf; a.priors = reinterpret_cast<const float4 *>(priors);
@@ -297,17 +296,11 @@ extern "C" int gssd_mbox_loss(const float *loc, const float *conf, const float *
     a.losses = losses; a.grad_loc = reinterpret_cast<float4 *>(grad_loc); a.grad_conf = grad_conf;
     a.pos_mask = pos_mask; a.neg_mask = neg_mask;
     a.partials = reinterpret_cast<double *>(ws);
-    a.slice = ceil_div(P, S);
     cudaStream_t st = (cudaStream_t)stream;
     const bool gr = grad_loc != nullptr;
     const bool c2 = C == 2;
-#define GSSD_LOSS_CASE(C2_, CL_, GR_) if (c2 == C2_ && (S > 1) == CL_ && gr == GR_) return launch_loss<C2_, CL_, GR_>(a, S, g_max, st);
-    GSSD_LOSS_CASE(true, true, true) GSSD_LOSS_CASE(true, true, false)
-    GSSD_LOSS_CASE(true, false, true) GSSD_LOSS_CASE(true, false, false)
-    GSSD_LOSS_CASE(false, true, true) GSSD_LOSS_CASE(false, true, false)
-    GSSD_LOSS_CASE(false, false, true) GSSD_LOSS_CASE(false, false, false)
-#undef GSSD_LOSS_CASE
-    return GSSD_ERR_ARG;
+    if (c2) return gr ? launch_loss<true, true>(a, g_max, st) : launch_loss<true, false>(a, g_max, st);
+    return gr ? launch_loss<false, true>(a, g_max, st) : launch_loss<false, false>(a, g_max, st);
 }
 
 extern "C" int gssd_mbox_scale_grads(float *grad_loc, size_t n_loc, float *grad_conf, size_t n_conf,

@@ -122,27 +122,50 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
     const bool dbg = blockIdx.x == 0 && blockIdx.y == 0;
     GSSD_PHASE(match, 0, dbg);
 
-    // ---- IoU sweep: a disjoint (GT, prior) pair costs two min/max/sub per axis and one test ------------
-    for (int p = p0 + tid; p < p1; p += MATCH_NT) {
-        const float4 pb = point_form(a.priors[p]);
-        const float area_b = box_area(pb);
-        if (CONF_MAX) {
-            const float *row = a.conf + ((size_t)b * a.P + p) * a.C;
-            if (a.C == 2) {
-                const float2 v = *reinterpret_cast<const float2 *>(row);
-                cmax = fmaxf(cmax, fmaxf(v.x, v.y));
-            } else {
-                for (int c = 0; c < a.C; ++c) cmax = fmaxf(cmax, row[c]);
+    // ---- batch max of conf over this CTA's rows: a streaming, vectorised pass of its own ----------------
+    if (CONF_MAX && p1 > p0) {
+        const float *src = a.conf + ((size_t)b * a.P + p0) * a.C;
+        const size_t n = (size_t)(p1 - p0) * a.C;
+        size_t head = ((16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15) >> 2;   // floats up to 16-byte alignment
+        if (head > n) head = n;
+        const size_t n4 = (n - head) >> 2;
+        const float4 *src4 = reinterpret_cast<const float4 *>(src + head);
+        for (size_t i = tid; i < head; i += MATCH_NT) cmax = fmaxf(cmax, src[i]);
+        constexpr int U = 4;
+        for (size_t base = 0; base < n4; base += MATCH_NT * U) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const size_t i = base + (size_t)u * MATCH_NT + tid;
+                v[u] = i < n4 ? ldg_stream(src4 + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
             }
+#pragma unroll
+            for (int u = 0; u < U; ++u) cmax = fmaxf(cmax, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
         }
+        for (size_t i = head + 4 * n4 + tid; i < n; i += MATCH_NT) cmax = fmaxf(cmax, src[i]);
+    }
+
+    // ---- IoU sweep, one warp per 32 consecutive priors ------------------------------------------------------
+    // A disjoint (GT, prior) pair costs two min/max/sub per axis and one test.  With many GT boxes the 32
+    // priors of a warp (neighbouring cells / anchors) first test the GT list against their common bounding
+    // box, one GT per lane, and only the GT rows that hit it are swept.
+    const bool warp_cull = n_list >= MATCH_CULL_MIN_G;
+    const float4 far = make_float4(3e30f, 3e30f, 0.f, 0.f);
+    int pbase = p0 + warp * 32;
+    float4 nxt = (pbase + lane < p1) ? a.priors[pbase + lane] : far;
+    for (; pbase < p1; pbase += MATCH_NT) {
+        const int p = pbase + lane;
+        const bool valid = p < p1;
+        const float4 pb = point_form(nxt);
+        if (pbase + MATCH_NT < p1) nxt = (p + MATCH_NT < p1) ? a.priors[p + MATCH_NT] : far;   // prefetch
+        const float area_b = box_area(pb);
         float best = 0.f;                                        // IoU >= 0: row 0 wins an all-zero column
         int bidx = 0;
-        for (int q = 0; q < n_list; ++q) {
-            const int g = glist[q];
+        auto sweep_one = [&](int g) {
             const float4 t = sgt4[g];
             const float iw = __fsub_rn(fminf(t.z, pb.z), fmaxf(t.x, pb.x));
             const float ih = __fsub_rn(fminf(t.w, pb.w), fmaxf(t.y, pb.y));
-            if (iw > 0.f && ih > 0.f) {                          // rare: the boxes overlap
+            if (valid && iw > 0.f && ih > 0.f) {                 // rare: the boxes overlap
                 const float inter = __fmul_rn(iw, ih);
                 const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(sarea[g], area_b), inter));
                 if (iou > best) { best = iou; bidx = g; }        // first max over GT (torch.max dim 0)
@@ -157,8 +180,33 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
                     if (key > sbest[g]) atomicMax(&sbest[g], key);
                 }
             }
+        };
+        if (!warp_cull) {
+            for (int q = 0; q < n_list; ++q) sweep_one(glist[q]);
+        } else {
+            float bx1 = valid ? pb.x : INFINITY, by1 = valid ? pb.y : INFINITY;
+            float bx2 = valid ? pb.z : -INFINITY, by2 = valid ? pb.w : -INFINITY;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                bx1 = fminf(bx1, __shfl_xor_sync(FULL, bx1, o)); by1 = fminf(by1, __shfl_xor_sync(FULL, by1, o));
+                bx2 = fmaxf(bx2, __shfl_xor_sync(FULL, bx2, o)); by2 = fmaxf(by2, __shfl_xor_sync(FULL, by2, o));
+            }
+            for (int gb = 0; gb < n_list; gb += 32) {
+                const int q = gb + lane;
+                bool hit = false;
+                if (q < n_list) {
+                    const float4 t = sgt4[glist[q]];
+                    hit = fminf(t.z, bx2) > fmaxf(t.x, bx1) && fminf(t.w, by2) > fmaxf(t.y, by1);
+                }
+                unsigned m = __ballot_sync(FULL, hit);
+                while (m) {                                      // ascending GT row: first-max order is kept
+                    const int qq = gb + __ffs(m) - 1;
+                    m &= m - 1;
+                    sweep_one(glist[qq]);
+                }
+            }
         }
-        stag[p - p0] = (uint16_t)(bidx | (!(best < a.threshold) ? 0x8000 : 0));   // box_utils.py:108
+        if (valid) stag[p - p0] = (uint16_t)(bidx | (!(best < a.threshold) ? 0x8000 : 0));   // box_utils.py:108
     }
     __syncthreads();
     GSSD_PHASE(match, 1, dbg);
@@ -220,21 +268,15 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
     GSSD_PHASE(match, 4, dbg);
 }
 
-static int pick_cluster(int B, int P) {
-    // enough CTAs to cover the 148 SMs about twice, at most 8 per image, at least ~512 priors per CTA
-    int s = 1;
-    while (s < 8 && B * s < 296 && P / (s * 2) >= 512) s *= 2;
-    return s;
-}
-
 template <bool MAT, bool CMAX>
 static int launch_match(const MatchArgs &a_in, int B, int g_max, cudaStream_t stream) {
     MatchArgs a = a_in;
-    int S = pick_cluster(B, a.P);
-    a.slice = ceil_div(a.P, S);
-    size_t smem = match_smem_bytes(g_max, a.slice);
     auto kern = match_kernel<MAT, CMAX>;
     GSSD_RETURN_IF_CUDA(allow_max_smem(reinterpret_cast<const void *>(kern)));
+    const int slots = resident_ctas(reinterpret_cast<const void *>(kern), MATCH_NT, match_smem_bytes(g_max, ceil_div(a.P, 4)));
+    const int S = pick_cluster_size(B, a.P, slots, 256);
+    a.slice = ceil_div(a.P, S);
+    size_t smem = match_smem_bytes(g_max, a.slice);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(S, B, 1);
     cfg.blockDim = dim3(MATCH_NT, 1, 1);

@@ -1,6 +1,7 @@
 """box_utils — same functions and signatures as layers/box_utils.py of the reference, computed by
 libgssd_b200.so.  Tensors may live on the CPU or on a CUDA device; results come back on the device of
 the first argument.  There is no CPU implementation: a CUDA device is required."""
+import numpy as np
 import torch
 
 from .. import _lib
@@ -65,22 +66,25 @@ class _PinnedRing(object):
 
     def __init__(self, slots=8):
         self.bufs = [None] * slots
+        self.views = [None] * slots
         self.events = [None] * slots
         self.i = 0
         self.keep = []
 
     def get(self, nbytes):
+        """-> (pinned uint8 tensor, numpy uint8 view of it, slot)"""
         if torch.cuda.is_current_stream_capturing():
             buf = torch.empty((max(nbytes, 16),), dtype=torch.uint8).pin_memory()
             self.keep.append(buf)
-            return buf, None
+            return buf, buf.numpy(), None
         k = self.i
         self.i = (self.i + 1) % len(self.bufs)
         if self.events[k] is not None:
             self.events[k].synchronize()
         if self.bufs[k] is None or self.bufs[k].numel() < nbytes:
             self.bufs[k] = torch.empty((max(2 * nbytes, 4096),), dtype=torch.uint8).pin_memory()
-        return self.bufs[k], k
+            self.views[k] = self.bufs[k].numpy()
+        return self.bufs[k], self.views[k], k
 
     def sent(self, k):
         if k is not None:
@@ -104,67 +108,47 @@ class PackedTargets(object):
         return iter((self.gt, self.gt_off, self.sum_g, self.g_max))
 
 
-def pack_targets(truths_list, labels_list, dev):
-    """per-image (truths[G,4], labels[G]) -> PackedTargets on `dev`.  One pinned-buffer H2D copy carries
-    the offsets (and the rows too when the targets live on the CPU); no host synchronisation.
-    Raises IndexError for an image without boxes (the reference fails at box_utils.py:94)."""
-    B = len(truths_list)
-    offs = [0] * (B + 1)
-    g_max = 0
-    for i, t in enumerate(truths_list):
-        g = int(t.size(0)) if t.dim() > 0 else 0
-        if g == 0:
-            raise IndexError("match: an image has no ground-truth box")
-        offs[i + 1] = offs[i] + g
-        g_max = g if g > g_max else g_max
-    sum_g = offs[B]
-    on_cpu = not any(t.is_cuda for t in truths_list) and not any(l.is_cuda for l in labels_list)
-    n_rows = sum_g * 5 if on_cpu else 0
-    nbytes = 4 * (n_rows + B + 1)
-    buf, slot = _ring.get(nbytes)
-    host_i = buf[:nbytes].view(torch.int32)
-    host_i[n_rows:] = torch.tensor(offs, dtype=torch.int32)
-    if on_cpu:
-        host_f = buf[:4 * n_rows].view(torch.float32).view(sum_g, 5)
-        for i in range(B):
-            host_f[offs[i]:offs[i + 1], :4] = truths_list[i].detach().reshape(-1, 4)
-            host_f[offs[i]:offs[i + 1], 4] = labels_list[i].detach().reshape(-1)
-    staged = buf[:nbytes].to(dev, non_blocking=True)
-    _ring.sent(slot)
-    words = staged.view(torch.int32)
-    gt_off = words[n_rows:]
-    if on_cpu:
-        gt = staged[:4 * n_rows].view(torch.float32).view(sum_g, 5)
-    else:
-        rows = [torch.cat([t.detach().reshape(-1, 4).to(dev, torch.float32),
-                           l.detach().reshape(-1, 1).to(dev, torch.float32)], 1)
-                for t, l in zip(truths_list, labels_list)]
-        gt = (rows[0] if B == 1 else torch.cat(rows, 0)).contiguous()
-    return PackedTargets(gt, gt_off, sum_g, g_max, B)
+def _offsets(lens):
+    if min(lens) <= 0:
+        raise IndexError("match: an image has no ground-truth box")      # the reference fails at box_utils.py:94
+    offs = np.zeros(len(lens) + 1, np.int32)
+    np.cumsum(lens, out=offs[1:])
+    return offs
 
 
 def pack_target_list(targets, dev):
-    """list of [n_i,5] tensors (the DataLoader format, data_custom_v2.py:260-263) -> PackedTargets."""
+    """list of [n_i,5] tensors (the DataLoader format, data_custom_v2.py:260-263) -> PackedTargets on `dev`.
+    CPU targets travel in ONE pinned-buffer H2D copy (rows + offsets); CUDA targets are concatenated on the
+    device and only the offsets are uploaded.  No host synchronisation either way."""
     if isinstance(targets, PackedTargets):
         return targets
-    if all((not t.is_cuda) for t in targets):
-        return pack_targets([t[:, :-1] for t in targets], [t[:, -1] for t in targets], dev)
-    # CUDA targets: one cat of the whole rows instead of one per image
     B = len(targets)
-    offs = [0] * (B + 1)
-    g_max = 0
-    for i, t in enumerate(targets):
-        g = int(t.size(0)) if t.dim() > 0 else 0
-        if g == 0:
-            raise IndexError("match: an image has no ground-truth box")
-        offs[i + 1] = offs[i] + g
-        g_max = max(g_max, g)
-    buf, slot = _ring.get(4 * (B + 1))
-    buf[:4 * (B + 1)].view(torch.int32).copy_(torch.tensor(offs, dtype=torch.int32))
-    gt_off = buf[:4 * (B + 1)].to(dev, non_blocking=True).view(torch.int32)
+    lens = [int(t.shape[0]) if t.dim() == 2 else 0 for t in targets]
+    offs = _offsets(lens)
+    sum_g, g_max = int(offs[B]), max(lens)
+    on_cpu = not any(t.is_cuda for t in targets)
+    n_rows = sum_g * 5 if on_cpu else 0
+    nbytes = 4 * (n_rows + B + 1)
+    buf, view, slot = _ring.get(nbytes)
+    if on_cpu:
+        np.concatenate([t.detach().numpy() for t in targets], axis=0,
+                       out=view[:4 * n_rows].view(np.float32).reshape(sum_g, 5), casting="unsafe")
+    view[4 * n_rows:nbytes].view(np.int32)[:] = offs
+    staged = buf[:nbytes].to(dev, non_blocking=True)
     _ring.sent(slot)
-    gt = torch.cat([t.detach().to(dev) for t in targets], 0).to(torch.float32).contiguous()
-    return PackedTargets(gt, gt_off, offs[B], g_max, B)
+    gt_off = staged[4 * n_rows:].view(torch.int32)
+    if on_cpu:
+        gt = staged[:4 * n_rows].view(torch.float32).view(sum_g, 5)
+    else:
+        gt = torch.cat([t.detach().to(dev) for t in targets], 0).to(torch.float32).contiguous()
+    return PackedTargets(gt, gt_off, sum_g, g_max, B)
+
+
+def pack_targets(truths_list, labels_list, dev):
+    """per-image (truths[G,4], labels[G]) pairs -> PackedTargets (the argument form of box_utils.match)."""
+    rows = [torch.cat([t.detach().reshape(-1, 4).float(), l.detach().reshape(-1, 1).float().to(t.device)], 1)
+            for t, l in zip(truths_list, labels_list)]
+    return pack_target_list(rows, dev)
 
 
 def match(threshold, truths, priors, variances, labels, loc_t, conf_t, idx):

@@ -67,8 +67,10 @@ class _MultiBoxLossFn(torch.autograd.Function):
             return (None,) * 12
         lib = _lib.load()
         with torch.cuda.device(grad_loc.device):
-            g_l = g_l.to(device=grad_loc.device, dtype=torch.float32).contiguous()
-            g_c = g_c.to(device=grad_loc.device, dtype=torch.float32).contiguous()
+            if not (g_l.is_cuda and g_l.dtype == torch.float32):
+                g_l = g_l.to(device=grad_loc.device, dtype=torch.float32)
+            if not (g_c.is_cuda and g_c.dtype == torch.float32):
+                g_c = g_c.to(device=grad_loc.device, dtype=torch.float32)
             _lib.check(lib.gssd_mbox_scale_grads(grad_loc.data_ptr(), grad_loc.numel(), grad_conf.data_ptr(),
                                                  grad_conf.numel(), g_l.data_ptr(), g_c.data_ptr(), _lib.stream()),
                        "gssd_mbox_scale_grads")
