@@ -189,6 +189,12 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
+def dbg(msg):
+    if os.environ.get("BENCH_DEBUG"):
+        sys.stderr.write("[bench r%s %.2f] %s\n" % (os.environ.get("RANK", "0"), time.perf_counter(), msg))
+        sys.stderr.flush()
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -206,6 +212,7 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.require_cuda()
+    dbg('init done')
 
     priors = PriorBox(config.ALL[a.priors]).forward(device="cuda")
     a.P = P = priors.shape[0]
@@ -243,6 +250,7 @@ def run_ours(a):
     step_device(dsets[0])
     torch.cuda.synchronize()
     kernels_per_step = _lib.launch_count() - n0
+    dbg('eager steps ok, kernels/step=%d' % kernels_per_step)
 
     graphs, use_graph = None, not a.no_graph
     if use_graph:
@@ -263,6 +271,7 @@ def run_ours(a):
                 pool = pool or g.pool()
                 graphs.append(g)
             torch.cuda.synchronize()
+            dbg('graphs captured')
         except Exception as e:                              # pragma: no cover
             sys.stderr.write("bench: CUDA-graph capture failed (%s); timing eager calls\n" % e)
             graphs, use_graph = None, False
@@ -281,14 +290,22 @@ def run_ours(a):
 
     # ---- timed region: device-resident --------------------------------------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
+    # W warm-up steps, then more in chunks until >= 0.5 s have passed so that the clocks have ramped; the
+    # ranks agree on every extra chunk (the steps contain a collective, so the counts must match)
     t_w = time.perf_counter()
-    i = 0
-    while i < max(3, a.warmup) or time.perf_counter() - t_w < 0.5:     # W steps and >= 0.5 s: clocks have ramped
+    for i in range(max(3, a.warmup)):
         run_step(i)
-        i += 1
-        if i % 64 == 0:
-            torch.cuda.synchronize()
+    for _ in range(200):
+        torch.cuda.synchronize()
+        more = torch.tensor([1.0 if time.perf_counter() - t_w < 0.5 else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(more, op=dist.ReduceOp.MAX)
+        if float(more) == 0.0:
+            break
+        for i in range(64):
+            run_step(i)
     barrier()
+    dbg('warm-up done')
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_launch0 = _lib.launch_count()
     e0.record()
@@ -297,6 +314,7 @@ def run_ours(a):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    dbg('timed region done')
     eager_launches = _lib.launch_count() - n_launch0
     gpu_launches = kernels_per_step * a.steps if graphs is not None else eager_launches
 
@@ -338,6 +356,7 @@ def run_ours(a):
     e2e_s = time.perf_counter() - t0
     barrier()
     clocks = sampler.stop() if sampler else None
+    dbg('e2e done')
 
     # ---- per-kernel durations (CUDA events on the launch stream, GPU kept busy so launches never starve) ----
     kern = time_kernels(a, lib, _lib, torch, dev, priors, dsets, pack_targets, B, P) if rank == 0 else None
@@ -380,8 +399,21 @@ def run_ours(a):
             line["roofline_sweep"] = sweep(a, lib, _lib, torch, dev, pack_targets)
         print(json.dumps(line), flush=True)
     if world > 1:
+        # graphs that captured NCCL work must be gone before the communicator is torn down; a watchdog
+        # guarantees the ranks exit even if the teardown stalls (results are already printed)
         dist.barrier()
-        dist.destroy_process_group()
+        graphs = None
+        for d in dsets:
+            d.pop("result", None)
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        try:
+            dist.destroy_process_group()
+        finally:
+            sys.stdout.flush(); sys.stderr.flush()
+            os._exit(0)
 
 
 def time_kernels(a, lib, _lib, torch, dev, priors, dsets, pack_targets, B, P, iters=None):

@@ -5,15 +5,9 @@ import torch
 import torch.nn as nn
 
 from ... import _lib
+from ... import dist as gdist
 from ...config import v2 as cfg
 from ..box_utils import pack_target_list
-
-
-def _dist_world():
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized():
-        return dist, dist.get_world_size()
-    return None, 1
 
 
 class _MultiBoxLossFn(torch.autograd.Function):
@@ -36,10 +30,9 @@ class _MultiBoxLossFn(torch.autograd.Function):
         # DataParallel semantics of the reference: x_max and N are over the GLOBAL batch
         # (train_lesion_multiphase_v2.py:242-246 -> multibox_loss.py:117, box_utils.py:167).
         gstats, n_g = None, 0
-        dist, world = _dist_world()
-        if world > 1 and group is not False:
-            gstats = torch.empty((world * _lib.STATS_HEADER_BYTES,), dtype=torch.uint8, device=dev)
-            dist.all_gather_into_tensor(gstats, stats[:_lib.STATS_HEADER_BYTES], group=group or None)
+        _, world, _ = gdist.world(group)
+        if world > 1:
+            gstats = gdist.all_gather_headers(stats[:_lib.STATS_HEADER_BYTES], group)
             n_g = world
         losses = torch.empty((2,), dtype=torch.float32, device=dev)
         grad_loc = torch.empty_like(loc) if need_grad else None

@@ -267,7 +267,10 @@ EXPORT int gssd_oracle_multibox_loss(
         uint8_t *pos_out /* [B,P] opt */, uint8_t *neg_out /* [B,P] opt */,
         float *key_out /* [B,P] opt: mining key after loss_c[pos]=0 */,
         float *kth_gap_out /* [B] opt: key[k-1]-key[k] of the sorted keys (0 = tie at the cut) */,
-        float *grad_loc /* [B,P,4] opt */, float *grad_conf /* [B,P,C] opt */) {
+        float *grad_loc /* [B,P,4] opt */, float *grad_conf /* [B,P,C] opt */,
+        const float *x_max_override /* opt: batch-global max of conf when this is one shard of a batch */,
+        const int32_t *n_override /* opt: batch-global number of positives */,
+        float *stats_out /* [2] opt: this batch's own (max of conf, number of positives) */) {
     size_t BP = (size_t)B * P;
     float *loc_t = (float *)malloc(sizeof(float) * 4 * BP);
     int64_t *conf_t = (int64_t *)malloc(sizeof(int64_t) * BP);
@@ -310,6 +313,9 @@ EXPORT int gssd_oracle_multibox_loss(
         }
         /* 91-99: mining key with the batch-global max, positives zeroed */
         float x_max = tensor_max(conf, BP * C);
+        if (stats_out) { stats_out[0] = x_max; stats_out[1] = (float)N; }
+        if (x_max_override) x_max = *x_max_override;
+        if (n_override) N = *n_override;
 #pragma omp parallel for
         for (size_t i = 0; i < BP; ++i) {
             float k = lse_row(conf + i * C, C, x_max) - conf[i * C + conf_t[i]];

@@ -174,13 +174,15 @@ def pack_targets(targets):
 
 
 def multibox_loss(loc, conf, priors, targets, threshold=0.5, negpos_ratio=3, variances=(0.1, 0.2),
-                  grads=True, extras=True):
-    """MultiBoxLoss.forward (+ autograd) -> dict."""
+                  grads=True, extras=True, x_max=None, n_total=None):
+    """MultiBoxLoss.forward (+ autograd) -> dict.  x_max / n_total: the batch-global max of conf and number
+    of positives when (loc, conf, targets) is one rank's shard of a larger batch."""
     loc, conf, priors = _f(loc), _f(conf), _f(priors)
     B, P, Cn = conf.shape
     gt, off = pack_targets(targets)
     losses = np.zeros(2, np.float32)
     num_pos = np.zeros(B, np.int32)
+    stats = np.zeros(2, np.float32)
     r = dict()
     if extras:
         r["loc_t"] = np.empty((B, P, 4), np.float32)
@@ -198,11 +200,13 @@ def multibox_loss(loc, conf, priors, targets, threshold=0.5, negpos_ratio=3, var
         C.c_float(threshold), C.c_int(negpos_ratio), C.c_float(variances[0]), C.c_float(variances[1]),
         _p(losses), _p(num_pos, C.c_int32), _p(g("loc_t")), _p(g("conf_t"), C.c_int64),
         _p(g("pos"), C.c_uint8), _p(g("neg"), C.c_uint8), _p(g("key")), _p(g("kth_gap")),
-        _p(g("grad_loc")), _p(g("grad_conf")))
+        _p(g("grad_loc")), _p(g("grad_conf")),
+        C.byref(C.c_float(x_max)) if x_max is not None else None,
+        C.byref(C.c_int32(n_total)) if n_total is not None else None, _p(stats))
     if rc == -5:
         raise IndexError("multibox_loss: image without ground truth")
     assert rc == 0, rc
-    r.update(loss_l=losses[0], loss_c=losses[1], num_pos=num_pos)
+    r.update(loss_l=losses[0], loss_c=losses[1], num_pos=num_pos, local_x_max=stats[0], local_n=int(stats[1]))
     return r
 
 
