@@ -25,6 +25,20 @@ class PriorCfg(C.Structure):
     ]
 
 
+class ConvDesc(C.Structure):
+    """`gssd_conv_desc` (include/gssd.h)."""
+    _fields_ = [
+        ("n_img", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+        ("c_in", C.c_int32), ("c_out", C.c_int32), ("groups", C.c_int32),
+        ("taps", C.c_int32), ("relu", C.c_int32),
+        ("x", C.c_void_p), ("w", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("row_ss_in", C.c_void_p), ("l2_eps", C.c_float),
+        ("y", C.c_void_p), ("row_ss_out", C.c_void_p), ("chan_sum", C.c_void_p),
+        ("loc", C.c_void_p), ("conf", C.c_void_p),
+        ("n_anchor", C.c_int32), ("n_cls", C.c_int32), ("prior_off", C.c_int32), ("n_priors", C.c_int32),
+    ]
+
+
 _P, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 _SIGS = {
     "gssd_abi_version": (C.c_int, []),
@@ -51,6 +65,11 @@ _SIGS = {
     "gssd_l2norm_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _SZ, _P]),
     "gssd_l2norm_bwd_ws_bytes": (_SZ, [_I, _I, _I]),
     "gssd_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I]),
+    "gssd_conv_igemm": (_I, [C.POINTER(ConvDesc), _P]),
+    "gssd_conv_pack_weights": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
+    "gssd_nchw_to_pm": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "gssd_pm_to_nchw": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "gssd_bn_act_pm": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _F, _I, _P, _P, _P]),
 }
 
 _lib = None

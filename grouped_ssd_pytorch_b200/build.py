@@ -11,8 +11,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgssd_b200.so")
-SOURCES = ["abi.cu", "boxes.cu", "match.cu", "loss.cu", "detect.cu"]
-HEADERS = ["common.cuh", "select.cuh", os.path.join("..", "..", "include", "gssd.h")]
+SOURCES = ["abi.cu", "boxes.cu", "match.cu", "loss.cu", "detect.cu", "gconv.cu"]
+HEADERS = ["common.cuh", "select.cuh", "tc.cuh", os.path.join("..", "..", "include", "gssd.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -22,6 +22,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xcudafe", "--diag_suppress=177",
     "-cudart", "static",
 ]
+# gconv.cu is the bf16 tensor-core path (1e-2 tolerance): no bit-exact contract, FMA contraction allowed
+PER_SOURCE_FLAGS = {"gconv.cu": ["-fmad=true"]}
 
 
 def _nvcc():
@@ -50,7 +52,8 @@ def build(force=False, verbose=False, phase_timing=False):
     extra = ["-DGSSD_PHASE_TIMING"] if phase_timing else []
     for s in SOURCES:
         o = os.path.join(HERE, "build", s.replace(".cu", "_dbg.o" if phase_timing else ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
+        flags = [f for f in NVCC_FLAGS if not (s in PER_SOURCE_FLAGS and f == "-fmad=false")] + PER_SOURCE_FLAGS.get(s, [])
+        cmd = [_nvcc()] + flags + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     failed = False

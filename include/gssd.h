@@ -197,6 +197,64 @@ GSSD_API int gssd_l2norm_bwd(const float *x, const float *weight, const float *n
 GSSD_API size_t gssd_l2norm_bwd_ws_bytes(int B, int Cn, int HW);
 
 /* ------------------------------------------------------------------------------------------
+ * Source block — replaces the per-source chain of SSD.forward,
+ * models/ssd_multiphase_custom_group.py:258-297 (source 1), 300-325 (source 2), 329-372 (sources
+ * 3-6) and the heads at 375-380:
+ *     grouped conv (groups = 4) -> BN -> ReLU -> [L2Norm, source 1] -> dense 1x1 fuse_X1 ->
+ *     bn_fuse_X1 -> ReLU -> loc.k / conf.k 3x3 -> permute(0,2,3,1) -> flatten -> concat
+ * as a chain of calls of ONE implicit-GEMM convolution kernel (tcgen05.mma with the accumulators in
+ * TMEM, operands staged by TMA; bf16 inputs, fp32 accumulation).
+ *
+ * Activations travel "pixel-major padded" (PM): bf16 [n_img][H+2][W+2][C], a zero 1-pixel border
+ * around every image, channels innermost.  Seen as a matrix X[rows, C] with
+ * rows = n_img*(H+2)*(W+2), a 3x3 / stride 1 / pad 1 tap (dy,dx) is the same matrix shifted by
+ * dy*(W+2)+dx rows, so every A tile is one 2-D TMA box; outputs are produced for every padded
+ * position and the border rows are written as zeros.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct gssd_conv_desc {
+    int32_t n_img, height, width;   /* interior extent H, W */
+    int32_t c_in, c_out, groups;    /* c_in/groups must be a multiple of 64 */
+    int32_t taps;                   /* 1 (1x1 conv) or 9 (3x3, stride 1, pad 1) */
+    int32_t relu;                   /* clamp at 0 after scale/shift */
+    const void  *x;                 /* bf16 PM [rows, c_in] */
+    const void  *w;                 /* bf16 [c_out, taps*c_in/groups], k = tap*(c_in/groups) + c, tap = ky*3+kx
+                                       (layout of gssd_conv_pack_weights) */
+    const float *scale;             /* [c_out] or NULL (= 1) */
+    const float *shift;             /* [c_out] or NULL (= 0):  y = acc*scale + shift  (conv bias, folded BN) */
+    const float *row_ss_in;         /* [rows] or NULL: acc *= 1/(sqrt(row_ss_in[m]) + l2_eps) first — the L2Norm of
+                                       the INPUT (l2norm.py:19-23) deferred past the GEMM; its per-channel weight
+                                       is folded into `w` by the caller */
+    float        l2_eps;
+    void        *y;                 /* bf16 PM [rows, c_out] or NULL */
+    float       *row_ss_out;        /* [rows] or NULL: sum_c y^2 of each pixel (the consumer's row_ss_in) */
+    float       *chan_sum;          /* [2*c_out] or NULL: += per-channel (sum, sum of squares) of acc*scale+shift over
+                                       the interior pixels — train-mode BatchNorm statistics; the caller zeroes it */
+    /* head mode (loc != NULL, y == NULL): output columns [0, 4A) go to loc and [4A, 4A + A*n_cls) to
+       conf at prior index prior_off + (h*W + w)*A + a — the NHWC flatten + concat of GSSD:375-380 */
+    float       *loc;               /* fp32 [n_img, n_priors, 4] */
+    float       *conf;              /* fp32 [n_img, n_priors, n_cls] */
+    int32_t      n_anchor, n_cls, prior_off, n_priors;
+} gssd_conv_desc;
+
+/* one convolution of the chain.  Returns GSSD_ERR_ARG / GSSD_ERR_LIMIT for shapes the kernel does not take. */
+GSSD_API int gssd_conv_igemm(const gssd_conv_desc *d_host, void *stream);
+
+/* weight packing: w[c_out, c_in/groups, kh, kw] fp32 (nn.Conv2d.weight) -> bf16 [c_out, taps*c_in/groups];
+ * in_scale[c_in] (optional) multiplies input channel c of every filter (L2Norm.weight folding). */
+GSSD_API int gssd_conv_pack_weights(const float *w, int c_out, int c_in_per_group, int groups, int taps,
+                           const float *in_scale, void *out_bf16, void *stream);
+/* layout converters between torch's NCHW fp32 and PM bf16 (borders written as zeros) */
+GSSD_API int gssd_nchw_to_pm(const float *x, int n_img, int c, int h, int w, void *y_bf16, void *stream);
+GSSD_API int gssd_pm_to_nchw(const void *x_bf16, int n_img, int c, int h, int w, float *y, void *stream);
+/* train-mode BatchNorm (+ReLU) applied in place on a PM tensor from the statistics a conv call left in
+ * chan_sum (biased variance, as F.batch_norm normalises): y = relu?((y - mean)*rstd*gamma + beta) on interior
+ * pixels; row_ss_out (optional) receives sum_c y^2 per pixel; mean_var_out[2*c] (optional) the batch mean and
+ * UNBIASED variance for the caller's running-stat update. */
+GSSD_API int gssd_bn_act_pm(void *y_bf16, int n_img, int c, int h, int w, const float *chan_sum,
+                   const float *gamma, const float *beta, float bn_eps, int relu,
+                   float *row_ss_out, float *mean_var_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * workspace sizing (host-only)
  * ---------------------------------------------------------------------------------------- */
 enum { GSSD_WS_LSE = 0, GSSD_WS_MATCH = 1, GSSD_WS_LOSS = 2, GSSD_WS_NMS = 3 };

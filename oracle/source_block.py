@@ -1,0 +1,116 @@
+"""numpy restatement of one GSSD source block — TEST INFRASTRUCTURE ONLY.
+
+Follows /root/reference/ssd_liverdet/models/ssd_multiphase_custom_group.py:
+  * grouped conv -> BN -> ReLU                      forward, lines 258-259 (vgg[30..32]) / 300-301 (vgg[47..49])
+  * L2Norm (source 1 only)                          line 281  -> layers/modules/l2norm.py:19-23
+  * fuse_X1 -> bn_fuse_X1 -> ReLU                   lines 290-297 / 317-323 / 365-369
+  * loc.k / conf.k 3x3, permute(0,2,3,1), flatten   lines 375-380
+nn.Conv2d / nn.BatchNorm2d semantics are torch's (cross-correlation, biased variance for the
+normalisation in training mode).  Pinned against the reference's own modules by
+tests/golden/make_golden_block.py -> tests/golden/source_block.npz.
+
+`emulate_bf16=True` rounds the operands of every convolution (activations and weights) to bfloat16 the
+way the CUDA path stores them, keeping fp32 accumulation: the tight comparison for the kernels; the
+plain fp32 result is the reference-faithful one (north-star tolerance 1e-2 relative for the bf16 conv).
+"""
+import numpy as np
+
+
+def bf16_round(a):
+    """round-to-nearest-even to bfloat16, returned as float32."""
+    a = np.ascontiguousarray(a, np.float32)
+    u = a.view(np.uint32)
+    r = ((u >> 16) & 1) + 0x7FFF
+    out = ((u + r) & 0xFFFF0000).astype(np.uint32)
+    return out.view(np.float32)
+
+
+def conv2d(x, w, b, groups=1, pad=0):
+    """x[N,C,H,W], w[Co,C/groups,kh,kw], stride 1 -> [N,Co,H+2p-kh+1,W+2p-kw+1] (fp32 accumulate in fp64 blocks)"""
+    N, C, H, W = x.shape
+    Co, Cg, kh, kw = w.shape
+    xp = np.pad(x, ((0, 0), (0, 0), (pad, pad), (pad, pad)))
+    Ho, Wo = H + 2 * pad - kh + 1, W + 2 * pad - kw + 1
+    out = np.zeros((N, Co, Ho, Wo), np.float64)
+    ng = Co // groups
+    for g in range(groups):
+        xg = xp[:, g * Cg:(g + 1) * Cg]
+        wg = w[g * ng:(g + 1) * ng].astype(np.float64)
+        for ky in range(kh):
+            for kx in range(kw):
+                patch = xg[:, :, ky:ky + Ho, kx:kx + Wo].astype(np.float64)          # [N,Cg,Ho,Wo]
+                out[:, g * ng:(g + 1) * ng] += np.einsum("nchw,oc->nohw", patch, wg[:, :, ky, kx], optimize=True)
+    if b is not None:
+        out += b.astype(np.float64)[None, :, None, None]
+    return out.astype(np.float32)
+
+
+def batch_norm(x, gamma, beta, mean, var, eps, training):
+    """F.batch_norm: training -> batch statistics (biased variance); returns (y, batch_mean, batch_var_unbiased)"""
+    if training:
+        m = x.astype(np.float64).mean(axis=(0, 2, 3))
+        v = x.astype(np.float64).var(axis=(0, 2, 3))
+        n = x.shape[0] * x.shape[2] * x.shape[3]
+        stats = (m.astype(np.float32), (v * n / max(n - 1, 1)).astype(np.float32))
+    else:
+        m, v = mean.astype(np.float64), var.astype(np.float64)
+        stats = None
+    y = (x - m[None, :, None, None]) / np.sqrt(v[None, :, None, None] + eps) * gamma[None, :, None, None] + beta[None, :, None, None]
+    return y.astype(np.float32), stats
+
+
+def l2norm(x, weight, eps=1e-10):
+    """l2norm.py:19-23"""
+    norm = np.sqrt((x.astype(np.float64) ** 2).sum(axis=1, keepdims=True)) + eps
+    return (weight[None, :, None, None] * (x / norm)).astype(np.float32)
+
+
+def source_block(x, prm, training=False, emulate_bf16=False):
+    """x[N,C,H,W] fp32 = input of the grouped conv (or, when prm has no 'gconv_w', the post-ReLU source itself).
+    prm: dict of numpy arrays named after the reference's parameters:
+       gconv_w/gconv_b/groups/gconv_pad, bn_{w,b,mean,var} (optional), l2norm_w (optional),
+       fuse_w/fuse_b, bn_fuse_{w,b,mean,var} (optional), loc_w/loc_b, conf_w/conf_b, bn_eps
+    -> dict(x_out, source, loc[N, H*W*A*4], conf[N, H*W*A*ncls])"""
+    rd = bf16_round if emulate_bf16 else (lambda a: a)
+    eps = float(prm.get("bn_eps", 1e-5))
+    if "gconv_w" in prm:
+        y = conv2d(rd(x), rd(prm["gconv_w"]), prm["gconv_b"], int(prm["groups"]), int(prm.get("gconv_pad", 1)))
+        if "bn_w" in prm:
+            if emulate_bf16 and training:
+                _, st = batch_norm(y, prm["bn_w"], prm["bn_b"], None, None, eps, True)
+                n = y.shape[0] * y.shape[2] * y.shape[3]
+                y, _ = batch_norm(rd(y), prm["bn_w"], prm["bn_b"], st[0], st[1] * (n - 1) / n, eps, False)
+            else:
+                y, _ = batch_norm(y, prm["bn_w"], prm["bn_b"], prm.get("bn_mean"), prm.get("bn_var"), eps, training)
+        x_out = np.maximum(y, 0)
+    else:
+        x_out = x
+    x_out = rd(x_out)
+    s = x_out
+    fuse_w = prm["fuse_w"]
+    if "l2norm_w" in prm:
+        if emulate_bf16:
+            # the CUDA path folds L2Norm.weight into the fuse weights and applies 1/(norm+eps) after the GEMM
+            fuse_w = fuse_w * prm["l2norm_w"][None, :, None, None]
+            norm = np.sqrt((x_out.astype(np.float64) ** 2).sum(axis=1, keepdims=True)) + 1e-10
+            z = conv2d(s, rd(fuse_w), None, 1, 0) / norm + prm["fuse_b"][None, :, None, None]
+            z = z.astype(np.float32)
+        else:
+            s = l2norm(x_out, prm["l2norm_w"])
+            z = conv2d(s, fuse_w, prm["fuse_b"], 1, 0)
+    else:
+        z = conv2d(s, rd(fuse_w), prm["fuse_b"], 1, 0)
+    if "bn_fuse_w" in prm:
+        if emulate_bf16 and training:
+            _, st = batch_norm(z, prm["bn_fuse_w"], prm["bn_fuse_b"], None, None, eps, True)
+            n = z.shape[0] * z.shape[2] * z.shape[3]
+            z, _ = batch_norm(rd(z), prm["bn_fuse_w"], prm["bn_fuse_b"], st[0], st[1] * (n - 1) / n, eps, False)
+        else:
+            z, _ = batch_norm(z, prm["bn_fuse_w"], prm["bn_fuse_b"], prm.get("bn_fuse_mean"), prm.get("bn_fuse_var"), eps, training)
+    src = rd(np.maximum(z, 0))
+    loc = conv2d(src, rd(prm["loc_w"]), prm["loc_b"], 1, 1)
+    conf = conv2d(src, rd(prm["conf_w"]), prm["conf_b"], 1, 1)
+    N = x.shape[0]
+    return dict(x_out=x_out, source=src,
+                loc=np.ascontiguousarray(loc.transpose(0, 2, 3, 1)).reshape(N, -1),
+                conf=np.ascontiguousarray(conf.transpose(0, 2, 3, 1)).reshape(N, -1))

@@ -87,3 +87,51 @@ def ohnm_unambiguous(key, pos, ratio):
         else:
             ok[b] = bool(pos[b][key[b] == ks[nn]].all())
     return ok
+
+
+# ---- source block -------------------------------------------------------------------------
+BLOCK_CASES = {
+    # tag: (seed, N, C_in, H, W, grouped conv (C_out, groups, k) or None, bn, l2norm, C_fuse, anchors, classes, training)
+    "s1": (61, 2, 512, 6, 6, (512, 4, 3), True, True, 512, 4, 2, False),        # conv4_3 -> L2Norm -> fuse_11 -> loc/conf[0]
+    "s1_train": (62, 2, 512, 7, 5, (512, 4, 3), True, True, 512, 4, 2, True),   # batch statistics
+    "s2": (63, 1, 1024, 5, 5, (1024, 4, 1), True, False, 1024, 6, 2, False),    # conv7 (1x1, groups 4) -> fuse_21 -> loc/conf[1]
+    "s4": (64, 2, 256, 5, 5, None, True, False, 256, 6, 2, False),              # extras source: fuse_41 -> loc/conf[3]
+    "s1_nobn": (65, 1, 512, 4, 9, (512, 4, 3), False, True, 512, 4, 3, False),  # batch_norm=False variant, 3 classes
+}
+
+
+def block_case(tag):
+    """-> (x[N,C,H,W] fp32 (bf16-representable, post-ReLU statistics), prm dict for oracle.source_block, training)"""
+    from oracle.source_block import bf16_round
+    seed, N, C, H, W, gc, bn, l2, Cf, A, ncls, training = BLOCK_CASES[tag]
+    r = np.random.RandomState(seed)
+    x = bf16_round(np.maximum(r.randn(N, C, H, W), 0).astype(np.float32))
+    prm = {"bn_eps": 1e-5}
+
+    def conv(co, ci, k, name):
+        fan = ci * k * k
+        prm[name + "_w"] = (r.randn(co, ci, k, k) * np.sqrt(2.0 / fan)).astype(np.float32)
+        prm[name + "_b"] = (r.randn(co) * 0.1).astype(np.float32)
+
+    def norm(c, name):
+        prm[name + "_w"] = r.uniform(0.5, 1.5, c).astype(np.float32)
+        prm[name + "_b"] = (r.randn(c) * 0.1).astype(np.float32)
+        prm[name + "_mean"] = (r.randn(c) * 0.2).astype(np.float32)
+        prm[name + "_var"] = r.uniform(0.5, 1.5, c).astype(np.float32)
+
+    c_mid = C
+    if gc is not None:
+        co, groups, k = gc
+        conv(co, C // groups, k, "gconv")
+        prm["groups"], prm["gconv_pad"] = groups, (k - 1) // 2
+        if bn:
+            norm(co, "bn")
+        c_mid = co
+    if l2:
+        prm["l2norm_w"] = (20.0 * r.uniform(0.8, 1.2, c_mid)).astype(np.float32)
+    conv(Cf, c_mid, 1, "fuse")
+    if bn:
+        norm(Cf, "bn_fuse")
+    conv(A * 4, Cf, 3, "loc")
+    conv(A * ncls, Cf, 3, "conf")
+    return x, prm, training
