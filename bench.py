@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="time eager API calls instead of CUDA-graph replay")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gconv", action="store_true", help="skip the tensor-core source-block measurement")
     ap.add_argument("--sweep", action="store_true", help="also report the kernels' roofline at larger batches")
     return ap.parse_args()
 
@@ -319,42 +320,81 @@ def run_ours(a):
     gpu_launches = kernels_per_step * a.steps if graphs is not None else eager_launches
 
     # ---- end to end: host buffers in, losses + detections out, every step -----------------------------------
+    # A 3-deep software pipeline over the public API: step i's H2D copies (pinned host -> device, copy stream) run
+    # beside step i-1's kernels and step i-2's D2H; every step still moves its own inputs in and its own results
+    # (two losses + the Detect tensor) out inside the timed region, and the host waits for a slot's results before it
+    # reuses the slot.
+    DEPTH = 3
     pin = []
     for s in host[:min(4, n_sets)]:
         pin.append(dict(loc=torch.from_numpy(s["loc"]).pin_memory(), conf=torch.from_numpy(s["conf"]).pin_memory(),
                         scores=torch.from_numpy(s["scores"]).pin_memory(),
                         targets=[torch.from_numpy(t) for t in s["targets"]]))
-    out_host = torch.empty((B, 2, TOP_K, 5), dtype=torch.float32).pin_memory()
-    loss_host = torch.empty((2,), dtype=torch.float32).pin_memory()
+    copy_in = torch.cuda.Stream()
+    slots = []
+    for _ in range(DEPTH):
+        slots.append(dict(loc=torch.empty((B, P, 4), device=dev).requires_grad_(), conf=torch.empty((B, P, 2), device=dev).requires_grad_(),
+                          scores=torch.empty((B, P, 2), device=dev),
+                          out_host=torch.empty((B, 2, TOP_K, 5), dtype=torch.float32).pin_memory(),
+                          loss_host=torch.empty((2,), dtype=torch.float32).pin_memory(),
+                          ev_in=torch.cuda.Event(), ev_free=torch.cuda.Event(), ev_done=torch.cuda.Event(), busy=False))
 
-    def step_e2e(h):
+    def step_e2e(h, sl):
         main = torch.cuda.current_stream()
-        loc = h["loc"].to(dev, non_blocking=True).requires_grad_()
-        scores = h["scores"].to(dev, non_blocking=True)
+        if sl["busy"]:
+            sl["ev_done"].synchronize()                          # this slot's previous results are on the host
+        with torch.cuda.stream(copy_in), torch.no_grad():
+            copy_in.wait_event(sl["ev_free"])                    # the kernels that read this slot's inputs are done
+            sl["loc"].copy_(h["loc"], non_blocking=True)
+            sl["scores"].copy_(h["scores"], non_blocking=True)
+            sl["conf"].copy_(h["conf"], non_blocking=True)
+            sl["ev_in"].record(copy_in)
+        main.wait_event(sl["ev_in"])
         side.wait_stream(main)
         with torch.cuda.stream(side):                            # Detect + its D2H beside the loss
-            out = Detect.apply(2, 0, TOP_K, CONF_THRESH, NMS_THRESH, loc.detach(), scores, priors)
-            out_host.copy_(out, non_blocking=True)
-        conf = h["conf"].to(dev, non_blocking=True).requires_grad_()
-        ll, lc = crit((loc, conf, priors), h["targets"])        # targets: CPU tensors, packed + copied inside
+            out = Detect.apply(2, 0, TOP_K, CONF_THRESH, NMS_THRESH, sl["loc"].detach(), sl["scores"], priors)
+            sl["out_host"].copy_(out, non_blocking=True)
+        sl["loc"].grad = None; sl["conf"].grad = None
+        ll, lc = crit((sl["loc"], sl["conf"], priors), h["targets"])   # targets: CPU tensors, packed + copied inside
         (ll + lc).backward()
-        loss_host.copy_(torch.stack([ll.detach(), lc.detach()]), non_blocking=True)
+        sl["loss_host"].copy_(torch.stack([ll.detach(), lc.detach()]), non_blocking=True)
         main.wait_stream(side)
-        main.synchronize()                                       # the step's results are on the host
-        return loss_host, out_host
+        sl["ev_free"].record(main)
+        sl["ev_done"].record(main)
+        sl["busy"] = True
+
+    def drain():
+        for sl in slots:
+            if sl["busy"]:
+                sl["ev_done"].synchronize()
+                sl["busy"] = False
 
     h2d = B * P * (16 + 8 + 8) + sum(t.numel() * 4 for t in pin[0]["targets"]) + 4 * (B + 1)
     d2h = 8 + B * 2 * TOP_K * 5 * 4
-    e2e_steps = max(10, min(a.steps, 200))
-    for i in range(3):
-        step_e2e(pin[i % len(pin)])
+    e2e_steps = max(10, min(a.steps, 300))
+    for i in range(2 * DEPTH):
+        step_e2e(pin[i % len(pin)], slots[i % DEPTH])
+    drain()
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        step_e2e(pin[i % len(pin)])
+        step_e2e(pin[i % len(pin)], slots[i % DEPTH])
+    drain()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    # the same step with no overlap between steps (latency of one step, informational)
+    t0 = time.perf_counter()
+    for i in range(20):
+        step_e2e(pin[i % len(pin)], slots[0])
+        drain()
+    e2e_serial_ms = (time.perf_counter() - t0) / 20 * 1e3
+    # a result sanity check: the pipelined path returns the same numbers as the device-resident path
+    step_e2e(pin[0], slots[0]); drain()
+    ll0, lc0, out0 = step_device(dsets[0])
+    torch.cuda.synchronize()
+    assert abs(float(slots[0]["loss_host"][0]) - float(ll0)) <= 1e-5 * abs(float(ll0)) + 1e-7, "e2e loss differs from the device-resident step"
+    assert torch.equal(slots[0]["out_host"], out0.cpu()), "e2e Detect output differs from the device-resident step"
     clocks = sampler.stop() if sampler else None
     dbg('e2e done')
 
@@ -385,7 +425,9 @@ def run_ours(a):
                        "kernels_per_step": kernels_per_step},
             "clocks": clocks,
             "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "pipeline": "3 steps in flight: H2D on a copy stream beside the previous step's kernels and D2H",
+                    "serial_ms_per_step": e2e_serial_ms},
             "gpu_launches": int(gpu_launches),
             "roofline": roof,
         }
@@ -395,6 +437,11 @@ def run_ours(a):
             done, dt = time_cpu(a, priors_np, host, 10 ** 9, 1, a.cpu_seconds)
             line["cpu_baseline"] = {"value": done * B / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": "%d steps of the batch-%d workload in %.1f s (oracle/gssd_oracle.c, OpenMP over images)" % (done, B, dt)}
+        if not a.no_gconv:
+            try:
+                line["gconv"] = time_gconv(a, torch, dev, B)
+            except Exception as e:                               # pragma: no cover
+                line["gconv"] = {"error": repr(e)}
         if a.sweep:
             line["roofline_sweep"] = sweep(a, lib, _lib, torch, dev, pack_targets)
         print(json.dumps(line), flush=True)
@@ -467,6 +514,57 @@ def time_kernels(a, lib, _lib, torch, dev, priors, dsets, pack_targets, B, P, it
         us = statistics.mean(e[0].elapsed_time(e[1]) for e in ev) * 1e3
         res.append({"name": name, "us": us, "bytes": nbytes, "gbs": nbytes / us / 1e3})
     return res
+
+
+def time_gconv(a, torch, dev, B):
+    """the source-1 block of configs[1] (batch B, 38x38, 512 channels) as three launches of the tcgen05/TMEM
+    implicit-GEMM kernel — vgg.30 grouped 3x3 (groups 4) -> fuse_11 1x1 (+deferred L2Norm) -> loc/conf 3x3 heads —
+    each timed alone with CUDA events over a ring of inputs larger than L2, against the measured bf16 GEMM peak."""
+    import torch.nn as nn
+    from grouped_ssd_pytorch_b200.layers.modules.source_block import PM, _Conv, conv_igemm
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, src = float(json.load(f)["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst: kernels timed alone)"
+    except Exception:
+        peak, src = 1590.0, "fallback (B200_PROFILING.md)"
+    torch.manual_seed(1111)
+    C, HW, A, NC = 512, 38, 4, 2
+    g = _Conv(nn.Conv2d(C, C, 3, padding=1, groups=4).to(dev), 4, dev=dev)
+    f = _Conv(nn.Conv2d(C, C, 1).to(dev), 1, dev=dev)
+    h = _Conv(nn.Conv2d(C, A * 4, 3, padding=1).to(dev), 1, extra=nn.Conv2d(C, A * NC, 3, padding=1).to(dev), dev=dev)
+    n_sets = 3                                                       # 3 x 52 MB activations > L2
+    xs = [PM.from_nchw(torch.relu(torch.randn(B, C, HW, HW, device=dev))) for _ in range(n_sets)]
+    P = HW * HW * A
+    loc, conf = torch.empty(B, P, 4, device=dev), torch.empty(B, P, NC, device=dev)
+    ss = torch.empty((xs[0].rows,), dtype=torch.float32, device=dev)
+    ys = [conv_igemm(x, g, relu=True, shift=g.bias, row_ss_out=ss) for x in xs]
+    zs = [conv_igemm(y, f, relu=True, shift=f.bias, row_ss_in=ss, l2_eps=1e-10) for y in ys]
+    specs = [("vgg.30 grouped 3x3 (groups 4, 512->512) + bias/BN-fold + ReLU + L2Norm row sums",
+              lambda i: conv_igemm(xs[i], g, relu=True, shift=g.bias, row_ss_out=ss), 2.0 * B * HW * HW * C * (C // 4) * 9),
+             ("fuse_11 1x1 (512->512) + deferred L2Norm + bias/BN-fold + ReLU",
+              lambda i: conv_igemm(ys[i], f, relu=True, shift=f.bias, row_ss_in=ss, l2_eps=1e-10), 2.0 * B * HW * HW * C * C),
+             ("loc.0 + conf.0 3x3 heads (512->24) + NHWC flatten/concat into loc/conf",
+              lambda i: conv_igemm(zs[i], h, relu=False, shift=h.bias, head=(loc, conf, A, NC, 0, P)), 2.0 * B * HW * HW * (A * (4 + NC)) * C * 9)]
+    rows, iters = [], 24
+    for name, fn, flops in specs:
+        for i in range(3):
+            fn(i % n_sets)
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        torch.cuda._sleep(int(2.5e7))
+        for i in range(iters):
+            ev[i][0].record()
+            fn(i % n_sets)
+            ev[i][1].record()
+        torch.cuda.synchronize()
+        us = statistics.mean(e[0].elapsed_time(e[1]) for e in ev) * 1e3
+        rows.append({"name": name, "us": us, "flops": flops, "tflops": flops / us / 1e6, "frac": flops / us / 1e6 / peak})
+    tot_us, tot_fl = sum(r["us"] for r in rows), sum(r["flops"] for r in rows)
+    return {"bound": "tensor", "workload": "configs[1] source 1: batch %d x 38x38 x 512, grouped conv -> fuse 1x1 -> heads, bf16 in / fp32 accumulate" % B,
+            "achieved": tot_fl / tot_us / 1e6, "peak": peak, "unit": "TFLOP/s", "frac": tot_fl / tot_us / 1e6 / peak, "peak_source": src,
+            "images_per_s": B / (tot_us * 1e-6), "total_us": tot_us,
+            "flops_note": "algorithmic flops of the 38x38 interior; the kernel also computes the 1-pixel border (40x40 rows, +10.8%)",
+            "kernels": rows}
 
 
 def sweep(a, lib, _lib, torch, dev, pack_targets):

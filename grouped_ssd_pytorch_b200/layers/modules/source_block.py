@@ -209,3 +209,84 @@ class SourceBlock(object):
         return x1, x.h * x.w * self.n_anchor
 
     __call__ = forward
+
+
+# ---- the model's forward with the source blocks swapped in ---------------------------------------------------
+def build_source_blocks(net):
+    """SourceBlocks for the six sources of a reference `SSD` (ssd_type gssd: no self-attention, no DCN), built from
+    its own modules.  Module indices follow multibox()'s `vgg_source` (ssd_multiphase_custom_group.py:499-502):
+    conv4_3 = vgg[30] (batch_norm) / vgg[21]; conv7 = vgg[-3] / vgg[-2]."""
+    if getattr(net, "use_self_attention", False) or getattr(net, "use_self_attention_base", False) or getattr(net, "use_dcn", False):
+        raise NotImplementedError("gssd_forward covers ssd_type 'gssd'; GSSD++ (self-attention / DCN) keeps the reference forward")
+    if not getattr(net, "use_fuseconv", True):
+        raise NotImplementedError("the source blocks expect use_fuseconv=True (the GSSD configuration)")
+    bn = bool(net.batch_norm)
+    vgg = net.vgg
+    i43 = 30 if bn else 21
+    i7 = len(vgg) - (3 if bn else 2)
+    nc = net.num_classes
+    blocks = [SourceBlock(vgg[i43], vgg[i43 + 1] if bn else None, net.L2Norm, net.fuse_11, net.bn_fuse_11 if bn else None,
+                          net.loc[0], net.conf[0], nc),
+              SourceBlock(vgg[i7], vgg[i7 + 1] if bn else None, None, net.fuse_21, net.bn_fuse_21 if bn else None,
+                          net.loc[1], net.conf[1], nc)]
+    for k in range(4):
+        blocks.append(SourceBlock(None, None, None, net.fuse_list1[k], net.bn_fuse_list1[k] if bn else None,
+                                  net.loc[2 + k], net.conf[2 + k], nc))
+    return blocks, (i43, i7)
+
+
+def gssd_forward(net, x, detect_args=(0, 200, 0.01, 0.45)):
+    """Forward of the reference's SSD (ssd_multiphase_custom_group.py:217-400, ssd_type gssd) with every source chain
+    — grouped conv / BN / ReLU / L2Norm / fuse 1x1 / BN / ReLU / loc+conf heads / permute / flatten / concat — run by
+    the tcgen05 source blocks; the rest of the backbone stays the model's own torch modules.  Forward only
+    (torch.no_grad): returns what `net(x)` returns — `(loc[B,P,4], conf[B,P,C], priors)` in the train phase,
+    `Detect` output `[B,C,top_k,5]` in the test phase (ssd_multiphase_custom_group.py:382-396).
+
+        net.forward = types.MethodType(gssd_forward, net)        # drop-in
+    """
+    import torch.nn.functional as F
+    from ..functions import Detect
+    _lib.require_cuda()
+    cache = getattr(net, "_gssd_blocks", None)
+    if cache is None:
+        cache = build_source_blocks(net)
+        net._gssd_blocks = cache
+    blocks, (i43, i7) = cache
+    bn = bool(net.batch_norm)
+    with torch.no_grad():
+        x = x.to(_lib.device_of(x))
+        B = x.size(0)
+        P = net.priors.size(0)
+        loc = torch.empty((B, P, 4), dtype=torch.float32, device=x.device)
+        conf = torch.empty((B, P, net.num_classes), dtype=torch.float32, device=x.device)
+        off = 0
+        for k in range(i43):                                     # GSSD:254-259, up to the input of conv4_3
+            x = net.vgg[k](x)
+        x1, n = blocks[0](x, loc, conf, off)                     # conv4_3 .. heads of source 1 (GSSD:258-297, 375-377)
+        off += n
+        x = x1.to_nchw()                                         # post-ReLU conv4_3 continues down the backbone
+        for k in range(i43 + (3 if bn else 2), i7):              # GSSD:300-301 up to the input of conv7
+            x = net.vgg[k](x)
+        x2, n = blocks[1](x, loc, conf, off)                     # conv7 .. heads of source 2 (GSSD:300-325)
+        off += n
+        x = x2.to_nchw()
+        si = 2
+        for k, v in enumerate(net.extras):                       # GSSD:329-372
+            x = v(x)
+            if bn:
+                if k % 2 == 1:
+                    x = F.relu(x, inplace=True)
+                is_source = k % 4 == 3
+            else:
+                x = F.relu(x, inplace=True)
+                is_source = k % 2 == 1
+            if is_source:
+                _, n = blocks[si](x, loc, conf, off)
+                off += n
+                si += 1
+        if off != P:
+            raise RuntimeError("the sources produced %d priors, the model has %d" % (off, P))
+        if net.phase == "test":                                  # GSSD:382-390
+            return Detect.apply(net.num_classes, detect_args[0], detect_args[1], detect_args[2], detect_args[3],
+                                loc, torch.softmax(conf, dim=-1), net.priors.to(x.device))
+        return loc, conf, net.priors

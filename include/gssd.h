@@ -255,6 +255,53 @@ GSSD_API int gssd_bn_act_pm(void *y_bf16, int n_img, int c, int h, int w, const 
                    float *row_ss_out, float *mean_var_out, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Host-buffer pipeline — the training-step / inference call of the hot path with HOST inputs and outputs:
+ * the H2D of train_lesion_multiphase_v2.py:198-200, the criterion call at :246 (MultiBoxLoss forward + the
+ * gradients of its two outputs) and Detect (ssd_multiphase_custom_group.py:384-390), `depth` steps in flight:
+ * step i's host->device copies run beside step i-1's kernels and step i-2's device->host copies.
+ * The caller owns the device arena (gssd_pipe_arena_bytes); the pipeline creates only streams and events.
+ * Host pointers should be page-locked (pageable memory works, the copies then serialise) and must stay valid
+ * until gssd_pipe_wait() of the ticket returns.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct gssd_pipe gssd_pipe;
+typedef struct gssd_pipe_cfg {
+    int32_t B, P, C, top_k, max_gt_rows, depth;       /* depth in [1, 8] */
+    float   match_thresh, var0, var1, conf_thresh, nms_thresh;
+    int32_t negpos_ratio;
+} gssd_pipe_cfg;
+typedef struct gssd_pipe_slot {                       /* device buffers of one in-flight step (inside the arena) */
+    float *loc, *conf, *scores, *gt;
+    int32_t *gt_off;
+    uint16_t *tags;
+    void *stats;                                      /* gssd_stats_bytes(B): header + num_pos[B] */
+    float *losses, *grad_loc, *grad_conf, *detect_out;
+    void *ws;
+    size_t ws_bytes;
+} gssd_pipe_slot;
+
+GSSD_API size_t  gssd_pipe_arena_bytes(const gssd_pipe_cfg *cfg_host);
+GSSD_API int     gssd_pipe_create(gssd_pipe **out, const gssd_pipe_cfg *cfg_host, const float *priors /* device [P,4] */,
+                         void *arena /* device */, size_t arena_bytes);
+GSSD_API void    gssd_pipe_destroy(gssd_pipe *p);
+GSSD_API int     gssd_pipe_slot_info(const gssd_pipe *p, int slot, gssd_pipe_slot *out_host);
+/* Enqueue one step.  Returns its ticket (>= 0; slot = ticket % depth) or a negative GSSD_ERR_* / -(1000 + cudaError_t).
+ * Blocks only when all `depth` slots are in flight (it then waits for the oldest step).  gt_host[sum_g,5] /
+ * gt_off_host[B+1] are the packed ground truth.  losses_host[2], detect_out_host[B,C,top_k,5]. */
+GSSD_API int64_t gssd_pipe_submit(gssd_pipe *p, const float *loc_host, const float *conf_host, const float *scores_host,
+                         const float *gt_host, const int32_t *gt_off_host, int sum_g, int g_max,
+                         float *losses_host, float *detect_out_host);
+/* The same step in two halves for data-parallel jobs: begin = H2D + matching (+ Detect and its D2H); the caller then
+ * all-gathers the 16-byte headers (slot.stats) of every rank on *stream_out; finish = loss + D2H of the losses. */
+GSSD_API int64_t gssd_pipe_begin(gssd_pipe *p, const float *loc_host, const float *conf_host, const float *scores_host,
+                        const float *gt_host, const int32_t *gt_off_host, int sum_g, int g_max,
+                        float *detect_out_host, void **stream_out);
+GSSD_API int     gssd_pipe_finish(gssd_pipe *p, int64_t ticket, const gssd_loss_stats *global_stats /* device */, int n_global_stats,
+                         float *losses_host);
+/* block until the step's outputs are in the host buffers; its gradients (slot.grad_loc / grad_conf) stay valid until
+ * the slot is reused, `depth` submits later */
+GSSD_API int     gssd_pipe_wait(gssd_pipe *p, int64_t ticket);
+
+/* ------------------------------------------------------------------------------------------
  * workspace sizing (host-only)
  * ---------------------------------------------------------------------------------------- */
 enum { GSSD_WS_LSE = 0, GSSD_WS_MATCH = 1, GSSD_WS_LOSS = 2, GSSD_WS_NMS = 3 };
