@@ -39,6 +39,20 @@ class ConvDesc(C.Structure):
     ]
 
 
+class PipeCfg(C.Structure):
+    """`gssd_pipe_cfg` (include/gssd.h)."""
+    _fields_ = [("B", C.c_int32), ("P", C.c_int32), ("C", C.c_int32), ("top_k", C.c_int32), ("max_gt_rows", C.c_int32),
+                ("depth", C.c_int32), ("match_thresh", C.c_float), ("var0", C.c_float), ("var1", C.c_float),
+                ("conf_thresh", C.c_float), ("nms_thresh", C.c_float), ("negpos_ratio", C.c_int32)]
+
+
+class PipeSlot(C.Structure):
+    """`gssd_pipe_slot` (include/gssd.h): device addresses as integers."""
+    _fields_ = [(n, C.c_void_p) for n in ("loc", "conf", "scores", "gt", "gt_off", "tags", "stats", "losses", "grad_loc",
+                                          "grad_conf", "detect_out", "ws")] + [("ws_bytes", C.c_size_t)]
+
+
+MAX_GT_PER_IMAGE = 128
 _P, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 _SIGS = {
     "gssd_abi_version": (C.c_int, []),
@@ -65,6 +79,14 @@ _SIGS = {
     "gssd_l2norm_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _SZ, _P]),
     "gssd_l2norm_bwd_ws_bytes": (_SZ, [_I, _I, _I]),
     "gssd_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I]),
+    "gssd_pipe_arena_bytes": (_SZ, [C.POINTER(PipeCfg)]),
+    "gssd_pipe_create": (_I, [C.POINTER(C.c_void_p), C.POINTER(PipeCfg), _P, _P, _SZ]),
+    "gssd_pipe_destroy": (None, [_P]),
+    "gssd_pipe_slot_info": (_I, [_P, _I, C.POINTER(PipeSlot)]),
+    "gssd_pipe_submit": (C.c_int64, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
+    "gssd_pipe_begin": (C.c_int64, [_P, _P, _P, _P, _P, _P, _I, _I, _P, C.POINTER(C.c_void_p)]),
+    "gssd_pipe_finish": (_I, [_P, C.c_int64, _P, _I, _P]),
+    "gssd_pipe_wait": (_I, [_P, C.c_int64]),
     "gssd_conv_igemm": (_I, [C.POINTER(ConvDesc), _P]),
     "gssd_conv_pack_weights": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "gssd_nchw_to_pm": (_I, [_P, _I, _I, _I, _I, _P, _P]),
