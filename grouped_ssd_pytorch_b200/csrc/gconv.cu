@@ -6,17 +6,15 @@
 //   weights     : bf16 W[c_out, taps*c_in/groups] (K-major)
 //   GEMM        : D[m, n] = sum_tap sum_c X[m + dy*(W+2) + dx, g*cg + c] * W[n, tap*cg + c]
 //
-// Kernel anatomy (256 threads, 1 CTA per SM, persistent over 128-row tiles):
-//   warp 0     TMA producer: per 64-channel K chunk one 128x64 box of X (row-shifted per tap; rows outside the
-//              tensor are zero-filled by TMA) and one BNx64 box of W into a STAGES-deep shared-memory ring
-//   warp 1     MMA issuer: one thread, 4 x tcgen05.mma (M=128, N=BN, K=16) per chunk, accumulating in TMEM;
-//              tcgen05.commit releases the ring slot / publishes the accumulator
-//   warp 2     TMEM allocation
-//   warps 4-7  epilogue: tcgen05.ld (thread = row, 32 columns at a time) -> scale/shift/ReLU/L2Norm bookkeeping ->
-//              bf16 PM store, or fp32 scatter into loc/conf (head mode)
-// A 128-row tile walks all its column units (group x n-tile) back to back through a ring of TMEM accumulator
-// slots, so the epilogue of unit u overlaps the MMAs of unit u+1 and per-row quantities (the L2Norm sum of
-// squares over ALL channels) stay in a register of the thread that owns the row.
+// Kernel anatomy (384 threads, 1 CTA per SM, persistent over work units = (row tile, group, n-tile)):
+//   warp 0      TMA producer: A ring of activation "slabs" (tile rows + halo, 64 channels; loaded once per channel
+//               chunk, every 3x3 tap reads it at a row offset) and B ring of weight-tile groups
+//   warp 1      MMA issuer: one elected lane, tcgen05.mma (M=128, N=BN, K=16) accumulating in TMEM; one mbarrier wait
+//               and one tcgen05.commit per B stage
+//   warp 2      TMEM allocation (two accumulator stages)
+//   warps 4-11  epilogue: tcgen05.ld (thread = row, 32 columns at a time) -> scale/shift/ReLU/L2Norm/BN-statistics ->
+//               bf16 PM tile through a TMA store, or fp32 scatter into loc/conf (head mode)
+// DESIGN.md section 4b has the measurements behind each choice.
 #include "common.cuh"
 #include "tc.cuh"
 
