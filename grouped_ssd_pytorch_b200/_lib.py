@@ -52,6 +52,14 @@ class PipeSlot(C.Structure):
                                           "grad_conf", "detect_out", "ws")] + [("ws_bytes", C.c_size_t)]
 
 
+XCHG_MAX_RANKS, XCHG_HANDLE_BYTES = 16, 64
+
+
+class Xchg(C.Structure):
+    """`gssd_xchg` (include/gssd.h)."""
+    _fields_ = [("peers", C.c_void_p * XCHG_MAX_RANKS), ("rank", C.c_int32), ("world", C.c_int32)]
+
+
 MAX_GT_PER_IMAGE = 128
 _P, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 _SIGS = {
@@ -79,6 +87,14 @@ _SIGS = {
     "gssd_l2norm_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _SZ, _P]),
     "gssd_l2norm_bwd_ws_bytes": (_SZ, [_I, _I, _I]),
     "gssd_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I]),
+    "gssd_xchg_create": (_I, [C.POINTER(C.c_void_p), _P]),
+    "gssd_xchg_open": (_I, [_P, C.POINTER(C.c_void_p)]),
+    "gssd_xchg_close": (_I, [_P]),
+    "gssd_xchg_destroy": (_I, [_P]),
+    "gssd_mbox_match_x": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _F, _P, _P, C.POINTER(Xchg), _P]),
+    "gssd_mbox_loss_x": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, C.POINTER(Xchg), _I, _F, _F,
+                              _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "gssd_pipe_set_xchg": (_I, [_P, C.POINTER(Xchg)]),
     "gssd_pipe_arena_bytes": (_SZ, [C.POINTER(PipeCfg)]),
     "gssd_pipe_create": (_I, [C.POINTER(C.c_void_p), C.POINTER(PipeCfg), _P, _P, _SZ]),
     "gssd_pipe_destroy": (None, [_P]),

@@ -87,6 +87,26 @@ static inline int resident_ctas(const void *kern, int threads, size_t smem) {
     return sms * per_sm;
 }
 
+// ---- peer exchange of the loss statistics (gssd_xchg, include/gssd.h) ---------------------------------------
+struct XSlot { uint32_t conf_max_ord; int32_t num_pos; uint32_t epoch; uint32_t pad; };
+struct XBuf {
+    XSlot slot[2][GSSD_XCHG_MAX_RANKS];     // [step parity][source rank]
+    uint32_t epoch;                          // this rank's step counter (advanced by the last CTA of stage 1)
+    uint32_t match_done;                     // CTA counter of the running stage-1 kernel
+};
+struct XDev {                                // kernel-argument image of gssd_xchg
+    XBuf *peers[GSSD_XCHG_MAX_RANKS];
+    int rank, world;                         // world == 0: exchange disabled
+};
+static inline XDev xdev_from(const gssd_xchg *x) {
+    XDev d = {};
+    if (x != nullptr) {
+        for (int r = 0; r < GSSD_XCHG_MAX_RANKS; ++r) d.peers[r] = reinterpret_cast<XBuf *>(x->peers[r]);
+        d.rank = x->rank; d.world = x->world;
+    }
+    return d;
+}
+
 // ---- optional phase timing (debug build only: -DGSSD_PHASE_TIMING, see tools/phase_times.py) ----------
 #ifdef GSSD_PHASE_TIMING
 // one array + accessor per translation unit (no relocatable device code in this build)

@@ -32,6 +32,7 @@ struct LossArgs {
     uint8_t *pos_mask, *neg_mask;
     double *partials;                       // [2 * n_ctas]
     int slice;
+    XDev x;                                 // peer exchange of the statistics (world == 0: off)
 };
 
 __device__ __forceinline__ float smooth_l1(float d, float &grad) {
@@ -62,7 +63,38 @@ __global__ void __launch_bounds__(LOSS_NT, 4) loss_kernel(LossArgs a) {
 
     // batch-global scalars: max over ranks of x_max, sum over ranks of N
     float x_max; int n_total;
-    {
+    if (a.x.world > 0) {
+        // peer exchange: wait until every rank's stage 1 has stored its statistics of THIS step into our buffer
+        __shared__ uint32_t s_mo; __shared__ int s_nt;
+        if (warp == 0) {
+            const XBuf *xl = a.x.peers[a.x.rank];
+            const uint32_t e = *reinterpret_cast<const volatile uint32_t *>(&xl->epoch);
+            uint32_t mo = 0; int nt = 0;
+            if (lane < a.x.world) {
+                const XSlot *sl = &xl->slot[e & 1][lane];
+                uint32_t seen;
+                unsigned long long t0 = 0;
+                unsigned spins = 0;
+                while (true) {
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(&sl->epoch) : "memory");
+                    if (seen == e) break;
+                    if ((++spins & 0xff) == 0) {                           // a rank that never arrives must not wedge the GPU
+                        unsigned long long now;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (t0 == 0) t0 = now;
+                        else if (now - t0 > 10000000000ull) __trap();
+                    }
+                }
+                mo = *reinterpret_cast<const volatile uint32_t *>(&sl->conf_max_ord);
+                nt = *reinterpret_cast<const volatile int32_t *>(&sl->num_pos);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) { mo = max(mo, __shfl_xor_sync(FULL, mo, o)); nt += __shfl_xor_sync(FULL, nt, o); }
+            if (lane == 0) { s_mo = mo; s_nt = nt; }
+        }
+        __syncthreads();
+        x_max = ord2f(s_mo); n_total = s_nt;
+    } else {
         uint32_t mo = a.stats[0]; int nt = (int)a.stats[1];
         if (a.gstats) {
             mo = 0; nt = 0;
@@ -272,14 +304,15 @@ using namespace gssd;
 
 extern "C" size_t gssd_stats_bytes(int B) { return sizeof(gssd_loss_stats) + sizeof(int32_t) * (size_t)(B > 0 ? B : 0); }
 
-extern "C" int gssd_mbox_loss(const float *loc, const float *conf, const float *priors, int B, int P, int C,
-                              const float *gt, const int32_t *gt_off, int sum_G, int g_max,
-                              const uint16_t *tags, void *stats_buf,
-                              const gssd_loss_stats *global_stats, int n_global_stats,
-                              int negpos_ratio, float var0, float var1,
-                              float *losses, float *grad_loc, float *grad_conf,
-                              uint8_t *pos_mask, uint8_t *neg_mask,
-                              void *ws, size_t ws_bytes, void *stream) {
+static int mbox_loss_impl(const float *loc, const float *conf, const float *priors, int B, int P, int C,
+                          const float *gt, const int32_t *gt_off, int sum_G, int g_max,
+                          const uint16_t *tags, void *stats_buf,
+                          const gssd_loss_stats *global_stats, int n_global_stats, const gssd_xchg *x,
+                          int negpos_ratio, float var0, float var1,
+                          float *losses, float *grad_loc, float *grad_conf,
+                          uint8_t *pos_mask, uint8_t *neg_mask,
+                          void *ws, size_t ws_bytes, void *stream) {
+    if (x && (x->world < 1 || x->world > GSSD_XCHG_MAX_RANKS || x->world > 32 || x->rank < 0 || x->rank >= x->world)) return GSSD_ERR_ARG;
     if (!loc || !conf || !priors || !gt || !gt_off || !tags || !stats_buf || !losses || !ws) return GSSD_ERR_ARG;
     if (B <= 0 || P <= 0 || sum_G <= 0 || g_max <= 0 || negpos_ratio < 0) return GSSD_ERR_ARG;
     if (C < 2 || C > GSSD_MAX_CLASSES) return GSSD_ERR_ARG;
@@ -296,11 +329,36 @@ extern "C" int gssd_mbox_loss(const float *loc, const float *conf, const float *
     a.losses = losses; a.grad_loc = reinterpret_cast<float4 *>(grad_loc); a.grad_conf = grad_conf;
     a.pos_mask = pos_mask; a.neg_mask = neg_mask;
     a.partials = reinterpret_cast<double *>(ws);
+    a.x = xdev_from(x);
     cudaStream_t st = (cudaStream_t)stream;
     const bool gr = grad_loc != nullptr;
     const bool c2 = C == 2;
     if (c2) return gr ? launch_loss<true, true>(a, g_max, st) : launch_loss<true, false>(a, g_max, st);
     return gr ? launch_loss<false, true>(a, g_max, st) : launch_loss<false, false>(a, g_max, st);
+}
+
+extern "C" int gssd_mbox_loss(const float *loc, const float *conf, const float *priors, int B, int P, int C,
+                              const float *gt, const int32_t *gt_off, int sum_G, int g_max,
+                              const uint16_t *tags, void *stats_buf,
+                              const gssd_loss_stats *global_stats, int n_global_stats,
+                              int negpos_ratio, float var0, float var1,
+                              float *losses, float *grad_loc, float *grad_conf,
+                              uint8_t *pos_mask, uint8_t *neg_mask,
+                              void *ws, size_t ws_bytes, void *stream) {
+    return mbox_loss_impl(loc, conf, priors, B, P, C, gt, gt_off, sum_G, g_max, tags, stats_buf, global_stats, n_global_stats, nullptr,
+                          negpos_ratio, var0, var1, losses, grad_loc, grad_conf, pos_mask, neg_mask, ws, ws_bytes, stream);
+}
+
+extern "C" int gssd_mbox_loss_x(const float *loc, const float *conf, const float *priors, int B, int P, int C,
+                                const float *gt, const int32_t *gt_off, int sum_G, int g_max,
+                                const uint16_t *tags, void *stats_buf, const gssd_xchg *x,
+                                int negpos_ratio, float var0, float var1,
+                                float *losses, float *grad_loc, float *grad_conf,
+                                uint8_t *pos_mask, uint8_t *neg_mask,
+                                void *ws, size_t ws_bytes, void *stream) {
+    if (!x) return GSSD_ERR_ARG;
+    return mbox_loss_impl(loc, conf, priors, B, P, C, gt, gt_off, sum_G, g_max, tags, stats_buf, nullptr, 0, x,
+                          negpos_ratio, var0, var1, losses, grad_loc, grad_conf, pos_mask, neg_mask, ws, ws_bytes, stream);
 }
 
 extern "C" int gssd_mbox_scale_grads(float *grad_loc, size_t n_loc, float *grad_conf, size_t n_conf,

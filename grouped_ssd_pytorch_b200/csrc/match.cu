@@ -9,6 +9,8 @@
 // memory, then the sequential "force match" (box_utils.py:101-105, last GT wins) is applied by one
 // thread, and the result is emitted either as 2-byte tags for the fused loss or as the reference's
 // materialised loc_t / conf_t.
+#include <string.h>
+
 #include "common.cuh"
 
 GSSD_PHASE_DECL(match)
@@ -27,6 +29,7 @@ struct MatchArgs {
     int32_t *num_pos;                         // [B] or null
     float4 *loc_t; int64_t *conf_t; int32_t *bti_out;   // materialised outputs or null
     int slice;                                // priors per CTA
+    XDev x;                                   // peer exchange of the statistics (world == 0: off)
 };
 
 // dynamic shared memory layout
@@ -261,6 +264,27 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
                 atomicAdd(reinterpret_cast<int *>(&a.stats[1]), tot);
                 if (CONF_MAX && p1 > p0) atomicMax(&a.stats[0], f2ord(mx));
             }
+            if (a.x.world > 0) {
+                // the LAST CTA of the grid publishes this rank's statistics into every peer's exchange buffer
+                XBuf *xl = a.x.peers[a.x.rank];
+                __threadfence();
+                const unsigned done = atomicAdd(&xl->match_done, 1u);
+                if (done == gridDim.x * gridDim.y - 1) {
+                    __threadfence();
+                    const uint32_t mo = atomicMax(&a.stats[0], 0u);
+                    const int np = atomicAdd(reinterpret_cast<int *>(&a.stats[1]), 0);
+                    const uint32_t e = xl->epoch + 1;
+                    xl->match_done = 0;
+                    for (int r = 0; r < a.x.world; ++r) {
+                        XSlot *dst = &a.x.peers[r]->slot[e & 1][a.x.rank];
+                        dst->conf_max_ord = mo; dst->num_pos = np;
+                    }
+                    __threadfence_system();                               // data before the epoch tags, system scope
+                    for (int r = 0; r < a.x.world; ++r)
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&a.x.peers[r]->slot[e & 1][a.x.rank].epoch), "r"(e) : "memory");
+                    xl->epoch = e;
+                }
+            }
         }
     }
     GSSD_PHASE(match, 3, dbg);
@@ -316,10 +340,11 @@ extern "C" int gssd_match(const float *priors, int P, const float *gt, const int
     return launch_match<true, false>(a, B, g_max, (cudaStream_t)stream);
 }
 
-extern "C" int gssd_mbox_match(const float *priors, int P, const float *conf, int C,
-                               const float *gt, const int32_t *gt_off, int B, int sum_G, int g_max,
-                               float threshold, uint16_t *tags, void *stats_buf, void *stream) {
+static int mbox_match_impl(const float *priors, int P, const float *conf, int C,
+                           const float *gt, const int32_t *gt_off, int B, int sum_G, int g_max,
+                           float threshold, uint16_t *tags, void *stats_buf, const gssd_xchg *x, void *stream) {
     if (!priors || !gt || !gt_off || !tags || !stats_buf) return GSSD_ERR_ARG;
+    if (x && (x->world < 1 || x->world > GSSD_XCHG_MAX_RANKS || x->rank < 0 || x->rank >= x->world)) return GSSD_ERR_ARG;
     int rc = check_match_sizes(P, B, sum_G, g_max);
     if (rc) return rc;
     if (conf && (C < 2 || C > GSSD_MAX_CLASSES)) return GSSD_ERR_ARG;
@@ -332,5 +357,41 @@ extern "C" int gssd_mbox_match(const float *priors, int P, const float *conf, in
     a.tags = tags;
     a.stats = reinterpret_cast<uint32_t *>(stats_buf);
     a.num_pos = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(stats_buf) + sizeof(gssd_loss_stats));
+    a.x = xdev_from(x);
     return conf ? launch_match<false, true>(a, B, g_max, st) : launch_match<false, false>(a, B, g_max, st);
 }
+
+extern "C" int gssd_mbox_match(const float *priors, int P, const float *conf, int C,
+                               const float *gt, const int32_t *gt_off, int B, int sum_G, int g_max,
+                               float threshold, uint16_t *tags, void *stats_buf, void *stream) {
+    return mbox_match_impl(priors, P, conf, C, gt, gt_off, B, sum_G, g_max, threshold, tags, stats_buf, nullptr, stream);
+}
+
+extern "C" int gssd_mbox_match_x(const float *priors, int P, const float *conf, int C,
+                                 const float *gt, const int32_t *gt_off, int B, int sum_G, int g_max,
+                                 float threshold, uint16_t *tags, void *stats_buf, const gssd_xchg *x, void *stream) {
+    if (!x) return GSSD_ERR_ARG;
+    return mbox_match_impl(priors, P, conf, C, gt, gt_off, B, sum_G, g_max, threshold, tags, stats_buf, x, stream);
+}
+
+// ---- exchange buffers ---------------------------------------------------------------------------------------
+extern "C" int gssd_xchg_create(void **xbuf_out, void *ipc_handle_out) {
+    if (!xbuf_out || !ipc_handle_out) return GSSD_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == GSSD_XCHG_HANDLE_BYTES, "handle size");
+    void *ptr = nullptr;
+    GSSD_RETURN_IF_CUDA(cudaMalloc(&ptr, sizeof(XBuf)));
+    cudaError_t e = cudaMemset(ptr, 0, sizeof(XBuf));
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(ipc_handle_out), ptr);
+    if (e != cudaSuccess) { cudaFree(ptr); return (int)e; }
+    *xbuf_out = ptr;
+    return GSSD_OK;
+}
+extern "C" int gssd_xchg_open(const void *ipc_handle, void **peer_ptr_out) {
+    if (!ipc_handle || !peer_ptr_out) return GSSD_ERR_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    GSSD_RETURN_IF_CUDA(cudaIpcOpenMemHandle(peer_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return GSSD_OK;
+}
+extern "C" int gssd_xchg_close(void *peer_ptr) { return peer_ptr ? (int)cudaIpcCloseMemHandle(peer_ptr) : GSSD_ERR_ARG; }
+extern "C" int gssd_xchg_destroy(void *xbuf) { return xbuf ? (int)cudaFree(xbuf) : GSSD_ERR_ARG; }

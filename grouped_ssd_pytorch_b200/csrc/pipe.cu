@@ -14,6 +14,8 @@ struct gssd_pipe {
     bool busy[8], begun[8];
     int g_sum[8], g_max[8];
     int64_t next;
+    bool use_x;
+    gssd_xchg x;
 };
 
 namespace {
@@ -74,7 +76,10 @@ int64_t begin_step(gssd_pipe *p, const float *loc_h, const float *conf_h, const 
     PIPE_CUDA(cudaMemcpyAsync(s.gt_off, gt_off_h, (size_t)(c.B + 1) * 4, cudaMemcpyHostToDevice, p->s_copy));
     PIPE_CUDA(cudaEventRecord(p->ev_in[k], p->s_copy));
     PIPE_CUDA(cudaStreamWaitEvent(p->s_main, p->ev_in[k], 0));
-    PIPE_RC(gssd_mbox_match(p->priors, c.P, s.conf, c.C, s.gt, s.gt_off, c.B, sum_g, g_max, c.match_thresh, s.tags, s.stats, p->s_main));
+    if (p->use_x)
+        PIPE_RC(gssd_mbox_match_x(p->priors, c.P, s.conf, c.C, s.gt, s.gt_off, c.B, sum_g, g_max, c.match_thresh, s.tags, s.stats, &p->x, p->s_main));
+    else
+        PIPE_RC(gssd_mbox_match(p->priors, c.P, s.conf, c.C, s.gt, s.gt_off, c.B, sum_g, g_max, c.match_thresh, s.tags, s.stats, p->s_main));
     if (have_scores) {
         PIPE_CUDA(cudaStreamWaitEvent(p->s_side, p->ev_in[k], 0));
         PIPE_RC(gssd_detect(s.loc, s.scores, p->priors, c.B, c.P, c.C, c.top_k, c.conf_thresh, c.nms_thresh, c.var0, c.var1,
@@ -93,9 +98,14 @@ int64_t finish_step(gssd_pipe *p, int64_t ticket, const gssd_loss_stats *global_
     const int k = (int)(ticket % c.depth);
     if (!p->begun[k]) return GSSD_ERR_ARG;
     const gssd_pipe_slot &s = p->slot[k];
-    PIPE_RC(gssd_mbox_loss(s.loc, s.conf, p->priors, c.B, c.P, c.C, s.gt, s.gt_off, p->g_sum[k], p->g_max[k], s.tags, s.stats,
-                           global_stats, n_global, c.negpos_ratio, c.var0, c.var1, s.losses, s.grad_loc, s.grad_conf, nullptr, nullptr,
-                           s.ws, s.ws_bytes, p->s_main));
+    if (p->use_x && global_stats == nullptr)
+        PIPE_RC(gssd_mbox_loss_x(s.loc, s.conf, p->priors, c.B, c.P, c.C, s.gt, s.gt_off, p->g_sum[k], p->g_max[k], s.tags, s.stats,
+                                 &p->x, c.negpos_ratio, c.var0, c.var1, s.losses, s.grad_loc, s.grad_conf, nullptr, nullptr,
+                                 s.ws, s.ws_bytes, p->s_main));
+    else
+        PIPE_RC(gssd_mbox_loss(s.loc, s.conf, p->priors, c.B, c.P, c.C, s.gt, s.gt_off, p->g_sum[k], p->g_max[k], s.tags, s.stats,
+                               global_stats, n_global, c.negpos_ratio, c.var0, c.var1, s.losses, s.grad_loc, s.grad_conf, nullptr, nullptr,
+                               s.ws, s.ws_bytes, p->s_main));
     PIPE_CUDA(cudaMemcpyAsync(losses_h, s.losses, 8, cudaMemcpyDeviceToHost, p->s_main));
     PIPE_CUDA(cudaStreamWaitEvent(p->s_main, p->ev_side[k], 0));             // Detect and its D2H belong to the step
     PIPE_CUDA(cudaEventRecord(p->ev_free[k], p->s_main));
@@ -117,7 +127,7 @@ extern "C" int gssd_pipe_create(gssd_pipe **out, const gssd_pipe_cfg *cfg, const
     if (arena_bytes < gssd_pipe_arena_bytes(cfg)) return GSSD_ERR_WS;
     gssd_pipe *p = new (std::nothrow) gssd_pipe();
     if (!p) return GSSD_ERR_ARG;
-    p->cfg = *cfg; p->priors = priors; p->next = 0;
+    p->cfg = *cfg; p->priors = priors; p->next = 0; p->use_x = false;
     uint8_t *base = (uint8_t *)(((uintptr_t)arena + 255) & ~(uintptr_t)255);
     const size_t per = layout_slot(*cfg, nullptr, nullptr);
     cudaError_t e = cudaSuccess;
@@ -147,6 +157,14 @@ extern "C" void gssd_pipe_destroy(gssd_pipe *p) {
     }
     cudaStreamDestroy(p->s_copy); cudaStreamDestroy(p->s_main); cudaStreamDestroy(p->s_side);
     delete p;
+}
+
+extern "C" int gssd_pipe_set_xchg(gssd_pipe *p, const gssd_xchg *x) {
+    if (!p) return GSSD_ERR_ARG;
+    if (!x) { p->use_x = false; return GSSD_OK; }
+    if (x->world < 1 || x->world > GSSD_XCHG_MAX_RANKS || x->rank < 0 || x->rank >= x->world) return GSSD_ERR_ARG;
+    p->x = *x; p->use_x = true;
+    return GSSD_OK;
 }
 
 extern "C" int gssd_pipe_slot_info(const gssd_pipe *p, int slot, gssd_pipe_slot *out) {

@@ -37,6 +37,92 @@ def all_gather_headers(header, group=None):
     return out
 
 
+# ---- peer exchange over NVLink peer memory (include/gssd.h: gssd_xchg) --------------------------------------
+_exchanges = {}
+
+
+class PeerExchange(object):
+    """Every rank's 16-byte statistics slot buffer, peer-mapped into every other rank of the group (CUDA IPC): stage 1's
+    last CTA stores into all peers, stage 2 spins on the local copy — no collective call, graph-capturable."""
+
+    def __init__(self, group=None):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.require_cuda()
+        dist, ws, rank = world(group)
+        if ws > _lib.XCHG_MAX_RANKS:
+            raise RuntimeError("peer exchange supports up to %d ranks" % _lib.XCHG_MAX_RANKS)
+        self.lib, self.opened = lib, []
+        own = C.c_void_p()
+        handle = (C.c_ubyte * _lib.XCHG_HANDLE_BYTES)()
+        _lib.check(lib.gssd_xchg_create(C.byref(own), handle), "gssd_xchg_create")
+        self.own = own
+        mine = (bytes(handle), torch.cuda.current_device(), _hostname())
+        everyone = [None] * ws
+        dist.all_gather_object(everyone, mine, group=group)
+        if any(h[2] != mine[2] for h in everyone):
+            raise RuntimeError("peer exchange needs all ranks on one host")
+        x = _lib.Xchg()
+        x.rank, x.world = rank, ws
+        for r, (hb, _, _) in enumerate(everyone):
+            if r == rank:
+                x.peers[r] = own.value
+            else:
+                ptr = C.c_void_p()
+                buf = (C.c_ubyte * _lib.XCHG_HANDLE_BYTES).from_buffer_copy(hb)
+                _lib.check(lib.gssd_xchg_open(buf, C.byref(ptr)), "gssd_xchg_open")
+                self.opened.append(ptr)
+                x.peers[r] = ptr.value
+        self.x = x
+        dist.barrier(group=group)                                # every rank has mapped every buffer before first use
+
+    def close(self):
+        for ptr in self.opened:
+            self.lib.gssd_xchg_close(ptr)
+        self.opened = []
+        if self.own is not None and self.own.value:
+            self.lib.gssd_xchg_destroy(self.own)
+            self.own = None
+
+
+def _hostname():
+    import socket
+    return socket.gethostname()
+
+
+def peer_exchange(group=None):
+    """the PeerExchange of `group` (created on first use), or None when the exchange is off or unavailable:
+    GSSD_PEER_XCHG=0, a non-NCCL backend, ranks on several hosts, or no peer access between the GPUs."""
+    import os
+    dist, ws, _ = world(group)
+    if ws <= 1 or os.environ.get("GSSD_PEER_XCHG", "1") == "0" or not torch.cuda.is_available():
+        return None
+    key = id(group) if group is not None else 0
+    if key not in _exchanges:
+        ex = None
+        try:
+            if dist.get_backend(group) == "nccl":
+                ex = PeerExchange(group)
+        except Exception as e:                                   # fall back to the all-gather, on every rank alike
+            import warnings
+            warnings.warn("gssd: peer exchange unavailable (%s); using the NCCL all-gather" % e)
+            ex = None
+        ok = torch.tensor([1 if ex is not None else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok) == 0 and ex is not None:
+            ex.close()
+            ex = None
+        _exchanges[key] = ex
+    return _exchanges[key]
+
+
+def close_exchanges():
+    for ex in _exchanges.values():
+        if ex is not None:
+            ex.close()
+    _exchanges.clear()
+
+
 # ---- host mirrors of the device encodings (used by the tests and by tools) -----------------------------
 def f2ord(x):
     """float32 -> order-preserving uint32 (csrc/common.cuh: f2ord)."""

@@ -24,14 +24,23 @@ class _MultiBoxLossFn(torch.autograd.Function):
         st = _lib.stream()
         tags = torch.empty((B, P), dtype=torch.int16, device=dev)
         stats = torch.empty((_lib.STATS_HEADER_BYTES + 4 * B,), dtype=torch.uint8, device=dev)
-        _lib.check(lib.gssd_mbox_match(priors.data_ptr(), P, conf.data_ptr(), C, gt.data_ptr(), gt_off.data_ptr(),
-                                       B, sum_g, g_max, float(threshold), tags.data_ptr(), stats.data_ptr(), st),
-                   "gssd_mbox_match")
         # DataParallel semantics of the reference: x_max and N are over the GLOBAL batch
-        # (train_lesion_multiphase_v2.py:242-246 -> multibox_loss.py:117, box_utils.py:167).
+        # (train_lesion_multiphase_v2.py:242-246 -> multibox_loss.py:117, box_utils.py:167): the 16-byte statistics of
+        # every rank travel either through the peer exchange (NVLink peer stores from stage 1's last CTA) or through
+        # an all-gather between the stages.
         gstats, n_g = None, 0
         _, world, _ = gdist.world(group)
-        if world > 1:
+        ex = gdist.peer_exchange(group) if world > 1 else None
+        if ex is not None:
+            import ctypes
+            _lib.check(lib.gssd_mbox_match_x(priors.data_ptr(), P, conf.data_ptr(), C, gt.data_ptr(), gt_off.data_ptr(),
+                                             B, sum_g, g_max, float(threshold), tags.data_ptr(), stats.data_ptr(),
+                                             ctypes.byref(ex.x), st), "gssd_mbox_match_x")
+        else:
+            _lib.check(lib.gssd_mbox_match(priors.data_ptr(), P, conf.data_ptr(), C, gt.data_ptr(), gt_off.data_ptr(),
+                                           B, sum_g, g_max, float(threshold), tags.data_ptr(), stats.data_ptr(), st),
+                       "gssd_mbox_match")
+        if world > 1 and ex is None:
             gstats = gdist.all_gather_headers(stats[:_lib.STATS_HEADER_BYTES], group)
             n_g = world
         losses = torch.empty((2,), dtype=torch.float32, device=dev)
@@ -41,11 +50,18 @@ class _MultiBoxLossFn(torch.autograd.Function):
         neg = torch.empty((B, P), dtype=torch.uint8, device=dev) if masks else None
         ws_bytes = lib.gssd_workspace_bytes(_lib.WS_LOSS, B, P, C, sum_g, 0)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-        _lib.check(lib.gssd_mbox_loss(loc.data_ptr(), conf.data_ptr(), priors.data_ptr(), B, P, C,
-                                      gt.data_ptr(), gt_off.data_ptr(), sum_g, g_max, tags.data_ptr(), stats.data_ptr(),
-                                      _lib.ptr(gstats), n_g, int(negpos_ratio), float(variance[0]), float(variance[1]),
-                                      losses.data_ptr(), _lib.ptr(grad_loc), _lib.ptr(grad_conf),
-                                      _lib.ptr(pos), _lib.ptr(neg), ws.data_ptr(), ws_bytes, st), "gssd_mbox_loss")
+        if ex is not None:
+            _lib.check(lib.gssd_mbox_loss_x(loc.data_ptr(), conf.data_ptr(), priors.data_ptr(), B, P, C,
+                                            gt.data_ptr(), gt_off.data_ptr(), sum_g, g_max, tags.data_ptr(), stats.data_ptr(),
+                                            ctypes.byref(ex.x), int(negpos_ratio), float(variance[0]), float(variance[1]),
+                                            losses.data_ptr(), _lib.ptr(grad_loc), _lib.ptr(grad_conf),
+                                            _lib.ptr(pos), _lib.ptr(neg), ws.data_ptr(), ws_bytes, st), "gssd_mbox_loss_x")
+        else:
+            _lib.check(lib.gssd_mbox_loss(loc.data_ptr(), conf.data_ptr(), priors.data_ptr(), B, P, C,
+                                          gt.data_ptr(), gt_off.data_ptr(), sum_g, g_max, tags.data_ptr(), stats.data_ptr(),
+                                          _lib.ptr(gstats), n_g, int(negpos_ratio), float(variance[0]), float(variance[1]),
+                                          losses.data_ptr(), _lib.ptr(grad_loc), _lib.ptr(grad_conf),
+                                          _lib.ptr(pos), _lib.ptr(neg), ws.data_ptr(), ws_bytes, st), "gssd_mbox_loss")
         ctx.grads = (grad_loc, grad_conf)
         num_pos = stats[_lib.STATS_HEADER_BYTES:].view(torch.int32)
         aux = [t for t in (pos, neg, num_pos) if t is not None]

@@ -61,6 +61,10 @@ class HostPipeline(object):
         self._h, self._lib = h, lib
         self.group = process_group
         self._gathered = None
+        _, world, _ = gdist.world(process_group)
+        self._ex = gdist.peer_exchange(process_group) if world > 1 else None
+        if self._ex is not None:                                  # statistics over NVLink peer memory: one native call per step
+            _lib.check(lib.gssd_pipe_set_xchg(h, C.byref(self._ex.x)), "gssd_pipe_set_xchg")
 
     def host_buffers(self):
         return HostBuffers(self.B, self.P, self.C, self.top_k)
@@ -90,7 +94,7 @@ class HostPipeline(object):
         sc = bufs.scores.data_ptr() if detect else None
         det = bufs.detections.data_ptr() if detect else None
         _, world, _ = gdist.world(self.group)
-        if world <= 1:
+        if world <= 1 or self._ex is not None:
             t = lib.gssd_pipe_submit(h, bufs.loc.data_ptr(), bufs.conf.data_ptr(), sc, gt_p, off_p, sum_g, g_max,
                                      bufs.losses.data_ptr(), det)
             if t < 0:

@@ -167,6 +167,36 @@ GSSD_API int gssd_mbox_loss(const float *loc, const float *conf, const float *pr
                    uint8_t *pos_mask, uint8_t *neg_mask,
                    void *ws, size_t ws_bytes, void *stream);
 
+/* Peer exchange of the loss statistics (data-parallel jobs on one NVLink/NVSwitch box): instead of an all-gather
+ * between the two stages, the LAST CTA of stage 1 stores this rank's 16-byte statistics straight into every peer's
+ * exchange buffer (peer-mapped memory, one 16-byte slot per rank and step parity, epoch-tagged, system-scope
+ * release), and stage 2 spins on its LOCAL buffer until the slots of all ranks carry the current epoch.  No host
+ * involvement, legal inside CUDA graphs (the epoch lives in device memory), a few microseconds instead of a
+ * collective launch.  Every rank must issue the same sequence of stage-1 / stage-2 calls. */
+#define GSSD_XCHG_MAX_RANKS 16
+#define GSSD_XCHG_HANDLE_BYTES 64
+typedef struct gssd_xchg {
+    void   *peers[GSSD_XCHG_MAX_RANKS];   /* device pointers to the exchange buffer of every rank (own included) */
+    int32_t rank, world;
+} gssd_xchg;
+/* allocate (cudaMalloc) and zero this rank's exchange buffer; export it for the peers (cudaIpcMemHandle_t) */
+GSSD_API int gssd_xchg_create(void **xbuf_out, void *ipc_handle_out_host /* 64 bytes */);
+GSSD_API int gssd_xchg_open(const void *ipc_handle_host /* 64 bytes */, void **peer_ptr_out);
+GSSD_API int gssd_xchg_close(void *peer_ptr);
+GSSD_API int gssd_xchg_destroy(void *xbuf);
+/* the two stages of MultiBoxLoss with the peer exchange in between (same arguments as gssd_mbox_match /
+ * gssd_mbox_loss otherwise; global_stats is replaced by the exchange) */
+GSSD_API int gssd_mbox_match_x(const float *priors, int P, const float *conf, int C,
+                      const float *gt, const int32_t *gt_off, int B, int sum_G, int g_max,
+                      float threshold, uint16_t *tags, void *stats_buf, const gssd_xchg *x_host, void *stream);
+GSSD_API int gssd_mbox_loss_x(const float *loc, const float *conf, const float *priors, int B, int P, int C,
+                     const float *gt, const int32_t *gt_off, int sum_G, int g_max,
+                     const uint16_t *tags, void *stats_buf, const gssd_xchg *x_host,
+                     int negpos_ratio, float var0, float var1,
+                     float *losses, float *grad_loc, float *grad_conf,
+                     uint8_t *pos_mask, uint8_t *neg_mask,
+                     void *ws, size_t ws_bytes, void *stream);
+
 /* Backward helper: grad_loc *= g[0], grad_conf *= g[1] in place (g = upstream gradients of the two
  * scalar losses, device).  Touches no memory when g == (1,1), the `(loss_l+loss_c).backward()` case
  * of train_lesion_multiphase_v2.py:247-248. */
@@ -297,6 +327,8 @@ GSSD_API int64_t gssd_pipe_begin(gssd_pipe *p, const float *loc_host, const floa
                         float *detect_out_host, void **stream_out);
 GSSD_API int     gssd_pipe_finish(gssd_pipe *p, int64_t ticket, const gssd_loss_stats *global_stats /* device */, int n_global_stats,
                          float *losses_host);
+/* data-parallel: route the statistics through the peer exchange, so gssd_pipe_submit() serves world_size > 1 too */
+GSSD_API int     gssd_pipe_set_xchg(gssd_pipe *p, const gssd_xchg *x_host);
 /* block until the step's outputs are in the host buffers; its gradients (slot.grad_loc / grad_conf) stay valid until
  * the slot is reused, `depth` submits later */
 GSSD_API int     gssd_pipe_wait(gssd_pipe *p, int64_t ticket);

@@ -39,7 +39,8 @@ def _run(loc, conf, pri, tg, dev):
     return ll, lc, l.grad, c.grad, crit.last_masks
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, xchg):
+    os.environ["GSSD_PEER_XCHG"] = xchg
     import torch.distributed as dist
     from grouped_ssd_pytorch_b200 import dist as gdist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -52,21 +53,37 @@ def _worker(rank, world, port, q):
         ll, lc, gl, gc, m = _run(loc[sl], conf[sl], pri, tg[sl], dev)
         tot = torch.stack([ll.detach(), lc.detach()]).double()
         dist.all_reduce(tot)
-        q.put((rank, tot.cpu().numpy(), gl.cpu().numpy(), gc.cpu().numpy(), m["neg"].cpu().numpy()))
+        # the native host-buffer pipeline in its two-phase (begin / all-gather / finish) form gives the same step
+        from grouped_ssd_pytorch_b200.pipeline import HostPipeline
+        pipe = HostPipeline(sl.stop - sl.start, torch.from_numpy(pri).to(dev), depth=2, device=dev)
+        hb = pipe.host_buffers()
+        hb.loc.copy_(torch.from_numpy(loc[sl])); hb.conf.copy_(torch.from_numpy(conf[sl]))
+        for _ in range(3):
+            t = pipe.submit(hb, [torch.from_numpy(x) for x in tg[sl]], detect=False)
+            pipe.wait(t)
+        pgl, pgc = pipe.grads(t)
+        pipe_ok = bool(float(hb.losses[0]) == float(ll.detach()) and float(hb.losses[1]) == float(lc.detach())
+                       and torch.equal(pgl, gl) and torch.equal(pgc, gc))
+        pipe.close()
+        q.put((rank, tot.cpu().numpy(), gl.cpu().numpy(), gc.cpu().numpy(), m["neg"].cpu().numpy(), pipe_ok))
+        used = gdist.peer_exchange(None) is not None
+        assert used == (xchg == "1"), "peer exchange in use: %s, requested: %s" % (used, xchg)
         dist.barrier()
+        gdist.close_exchanges()
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpus_match_one_gpu():
+@pytest.mark.parametrize("xchg", ["1", "0"])                     # NVLink peer exchange / NCCL all-gather of the statistics
+def test_two_gpus_match_one_gpu(xchg):
     import torch.multiprocessing as mp
     from grouped_ssd_pytorch_b200 import dist as gdist
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, xchg)) for r in range(world)]
     for p in procs:
         p.start()
     got = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
@@ -76,7 +93,8 @@ def test_two_gpus_match_one_gpu():
     loc, conf, pri, tg = _inputs()
     ll, lc, gl, gc, m = _run(loc, conf, pri, tg, torch.device("cuda", 0))
     ref = np.array([ll.item(), lc.item()])
-    for rank, tot, g_l, g_c, neg in got:
+    for rank, tot, g_l, g_c, neg, pipe_ok in got:
+        assert pipe_ok, "HostPipeline (begin / all-gather / finish) differs from MultiBoxLoss on rank %d" % rank
         sl = gdist.shard(loc.shape[0], rank, world)
         np.testing.assert_allclose(tot, ref, rtol=1e-6)
         assert np.array_equal(neg, m["neg"][sl].cpu().numpy())
