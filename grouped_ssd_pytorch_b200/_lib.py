@@ -83,6 +83,8 @@ _SIGS = {
                             _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "gssd_mbox_scale_grads": (_I, [_P, _SZ, _P, _SZ, _P, _P, _P]),
     "gssd_detect": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P]),
+    "gssd_detect_logits": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P]),
+    "gssd_pipe_set_detect_logits": (_I, [_P, _I, _P]),
     "gssd_l2norm_fwd": (_I, [_P, _P, _I, _I, _I, _F, _P, _P, _P]),
     "gssd_l2norm_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _SZ, _P]),
     "gssd_l2norm_bwd_ws_bytes": (_SZ, [_I, _I, _I]),

@@ -28,6 +28,9 @@ struct DetArgs {
     // common
     int top_k, k2;          // k2 = next power of two >= top_k
     float nms_thresh;
+    // logits mode (gssd_detect_logits): conf holds raw class logits, the class score is softmax(conf + bias)[cl]
+    int logits;
+    float bias[GSSD_MAX_CLASSES];
 };
 
 struct DetShared {
@@ -87,6 +90,25 @@ __device__ void bitonic_sort_desc(unsigned long long *a, int n2) {
     }
 }
 
+// softmax over a row of class logits, the way torch's softmax kernel evaluates it (ssd_multiphase_custom_group.py:388):
+// subtract the row max, exp, sum in class order, IEEE divide
+__device__ __forceinline__ float softmax2_class1(float x0, float x1) {
+    const float m = fmaxf(x0, x1);
+    const float e0 = expf(__fsub_rn(x0, m)), e1 = expf(__fsub_rn(x1, m));
+    return __fdiv_rn(e1, __fadd_rn(e0, e1));
+}
+__device__ __forceinline__ float softmax_class(const float *row, const float *bias, int C, int cl) {
+    float m = -INFINITY;
+    for (int c = 0; c < C; ++c) m = fmaxf(m, __fadd_rn(__ldg(row + c), bias[c]));
+    float sum = 0.f, mine = 0.f;
+    for (int c = 0; c < C; ++c) {
+        const float e = expf(__fsub_rn(__fadd_rn(__ldg(row + c), bias[c]), m));
+        sum = __fadd_rn(sum, e);
+        if (c == cl) mine = e;
+    }
+    return __fdiv_rn(mine, sum);
+}
+
 // dynamic smem:  [ u32 keys[n] | (aliased later) u32 mask[top_k][words] ]  u64 ckey[max(k2, CAP)]  float4 box[top_k]  float area[top_k]
 template <bool NMS_MODE>
 __global__ void __launch_bounds__(DET_NT) detect_kernel(DetArgs a) {
@@ -143,6 +165,10 @@ __global__ void __launch_bounds__(DET_NT) detect_kernel(DetArgs a) {
                 for (int u = 0; u < U; ++u) {
                     const int q = base + u * DET_NT + tid;
                     sv[u] = q < n4 ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (a.logits) {                                         // fused softmax: (.y, .w) become the class-1 scores
+                        sv[u].y = softmax2_class1(__fadd_rn(sv[u].x, a.bias[0]), __fadd_rn(sv[u].y, a.bias[1]));
+                        sv[u].w = softmax2_class1(__fadd_rn(sv[u].z, a.bias[0]), __fadd_rn(sv[u].w, a.bias[1]));
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -164,6 +190,7 @@ __global__ void __launch_bounds__(DET_NT) detect_kernel(DetArgs a) {
                 for (int u = 0; u < U; ++u) {
                     const int p = base + u * DET_NT + tid;
                     sv[u] = p < n ? __ldg(src + (size_t)p * stride) : 0.f;
+                    if (!NMS_MODE && a.logits && p < n) sv[u] = softmax_class(a.conf + ((size_t)b * a.P + p) * a.C, a.bias, a.C, cl);
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -338,9 +365,9 @@ static int launch_detect(DetArgs &a, dim3 grid, cudaStream_t st) {
 
 using namespace gssd;
 
-extern "C" int gssd_detect(const float *loc, const float *conf, const float *priors, int B, int P, int C,
-                           int top_k, float conf_thresh, float nms_thresh, float var0, float var1,
-                           float *out, int32_t *count, int32_t *keep_idx, void *stream) {
+static int detect_impl(const float *loc, const float *conf, const float *class_bias, bool logits, const float *priors, int B, int P, int C,
+                       int top_k, float conf_thresh, float nms_thresh, float var0, float var1,
+                       float *out, int32_t *count, int32_t *keep_idx, void *stream) {
     if (!loc || !conf || !priors || !out) return GSSD_ERR_ARG;
     if (B <= 0 || P <= 0 || C < 1 || top_k <= 0) return GSSD_ERR_ARG;
     if (nms_thresh <= 0) return GSSD_ERR_VALUE;                     // detection_pytorch_ver_1point5.py:39-40
@@ -350,7 +377,23 @@ extern "C" int gssd_detect(const float *loc, const float *conf, const float *pri
     a.B = B; a.P = P; a.C = C; a.conf_thresh = conf_thresh; a.var0 = var0; a.var1 = var1;
     a.out = out; a.count = count; a.keep_idx = keep_idx;
     a.top_k = top_k; a.nms_thresh = nms_thresh;
+    a.logits = logits ? 1 : 0;
+    if (logits && class_bias) for (int c = 0; c < C; ++c) a.bias[c] = class_bias[c];
     return launch_detect<false>(a, dim3(C, B, 1), (cudaStream_t)stream);
+}
+
+extern "C" int gssd_detect(const float *loc, const float *conf, const float *priors, int B, int P, int C,
+                           int top_k, float conf_thresh, float nms_thresh, float var0, float var1,
+                           float *out, int32_t *count, int32_t *keep_idx, void *stream) {
+    return detect_impl(loc, conf, nullptr, false, priors, B, P, C, top_k, conf_thresh, nms_thresh, var0, var1, out, count, keep_idx, stream);
+}
+
+extern "C" int gssd_detect_logits(const float *loc, const float *conf_logits, const float *class_bias_host, const float *priors,
+                                  int B, int P, int C, int top_k, float conf_thresh, float nms_thresh, float var0, float var1,
+                                  float *out, int32_t *count, int32_t *keep_idx, void *stream) {
+    if (C < 2) return GSSD_ERR_ARG;
+    return detect_impl(loc, conf_logits, class_bias_host, true, priors, B, P, C, top_k, conf_thresh, nms_thresh, var0, var1, out, count,
+                       keep_idx, stream);
 }
 
 extern "C" int gssd_nms(const float *boxes, const float *scores, int n, float overlap, int top_k,

@@ -16,6 +16,8 @@ struct gssd_pipe {
     int64_t next;
     bool use_x;
     gssd_xchg x;
+    bool det_logits;
+    float class_bias[GSSD_MAX_CLASSES];
 };
 
 namespace {
@@ -62,11 +64,15 @@ int64_t begin_step(gssd_pipe *p, const float *loc_h, const float *conf_h, const 
     const gssd_pipe_slot &s = p->slot[k];
     const size_t BP = (size_t)c.B * c.P, n_loc = BP * 4 * 4, n_conf = BP * c.C * 4;
     PIPE_CUDA(cudaStreamWaitEvent(p->s_copy, p->ev_free[k], 0));             // the kernels that read this slot are done
-    const bool have_scores = scores_h != nullptr && det_h != nullptr;
+    const bool do_detect = det_h != nullptr && (p->det_logits || scores_h != nullptr);
+    const bool have_scores = do_detect && !p->det_logits;
     const bool adjacent = have_scores && (const uint8_t *)conf_h == (const uint8_t *)loc_h + align_up(n_loc) &&
                           (const uint8_t *)scores_h == (const uint8_t *)conf_h + align_up(n_conf);
+    const bool adjacent2 = !have_scores && (const uint8_t *)conf_h == (const uint8_t *)loc_h + align_up(n_loc);
     if (adjacent) {
         PIPE_CUDA(cudaMemcpyAsync(s.loc, loc_h, align_up(n_loc) + align_up(n_conf) + n_conf, cudaMemcpyHostToDevice, p->s_copy));
+    } else if (adjacent2) {
+        PIPE_CUDA(cudaMemcpyAsync(s.loc, loc_h, align_up(n_loc) + n_conf, cudaMemcpyHostToDevice, p->s_copy));
     } else {
         PIPE_CUDA(cudaMemcpyAsync(s.loc, loc_h, n_loc, cudaMemcpyHostToDevice, p->s_copy));
         PIPE_CUDA(cudaMemcpyAsync(s.conf, conf_h, n_conf, cudaMemcpyHostToDevice, p->s_copy));
@@ -80,10 +86,14 @@ int64_t begin_step(gssd_pipe *p, const float *loc_h, const float *conf_h, const 
         PIPE_RC(gssd_mbox_match_x(p->priors, c.P, s.conf, c.C, s.gt, s.gt_off, c.B, sum_g, g_max, c.match_thresh, s.tags, s.stats, &p->x, p->s_main));
     else
         PIPE_RC(gssd_mbox_match(p->priors, c.P, s.conf, c.C, s.gt, s.gt_off, c.B, sum_g, g_max, c.match_thresh, s.tags, s.stats, p->s_main));
-    if (have_scores) {
+    if (do_detect) {
         PIPE_CUDA(cudaStreamWaitEvent(p->s_side, p->ev_in[k], 0));
-        PIPE_RC(gssd_detect(s.loc, s.scores, p->priors, c.B, c.P, c.C, c.top_k, c.conf_thresh, c.nms_thresh, c.var0, c.var1,
-                            s.detect_out, nullptr, nullptr, p->s_side));
+        if (p->det_logits)
+            PIPE_RC(gssd_detect_logits(s.loc, s.conf, p->class_bias, p->priors, c.B, c.P, c.C, c.top_k, c.conf_thresh, c.nms_thresh,
+                                       c.var0, c.var1, s.detect_out, nullptr, nullptr, p->s_side));
+        else
+            PIPE_RC(gssd_detect(s.loc, s.scores, p->priors, c.B, c.P, c.C, c.top_k, c.conf_thresh, c.nms_thresh, c.var0, c.var1,
+                                s.detect_out, nullptr, nullptr, p->s_side));
         PIPE_CUDA(cudaMemcpyAsync(det_h, s.detect_out, (size_t)c.B * c.C * c.top_k * 5 * 4, cudaMemcpyDeviceToHost, p->s_side));
     }
     PIPE_CUDA(cudaEventRecord(p->ev_side[k], p->s_side));
@@ -127,7 +137,8 @@ extern "C" int gssd_pipe_create(gssd_pipe **out, const gssd_pipe_cfg *cfg, const
     if (arena_bytes < gssd_pipe_arena_bytes(cfg)) return GSSD_ERR_WS;
     gssd_pipe *p = new (std::nothrow) gssd_pipe();
     if (!p) return GSSD_ERR_ARG;
-    p->cfg = *cfg; p->priors = priors; p->next = 0; p->use_x = false;
+    p->cfg = *cfg; p->priors = priors; p->next = 0; p->use_x = false; p->det_logits = false;
+    for (int i = 0; i < GSSD_MAX_CLASSES; ++i) p->class_bias[i] = 0.f;
     uint8_t *base = (uint8_t *)(((uintptr_t)arena + 255) & ~(uintptr_t)255);
     const size_t per = layout_slot(*cfg, nullptr, nullptr);
     cudaError_t e = cudaSuccess;
@@ -157,6 +168,13 @@ extern "C" void gssd_pipe_destroy(gssd_pipe *p) {
     }
     cudaStreamDestroy(p->s_copy); cudaStreamDestroy(p->s_main); cudaStreamDestroy(p->s_side);
     delete p;
+}
+
+extern "C" int gssd_pipe_set_detect_logits(gssd_pipe *p, int enable, const float *class_bias) {
+    if (!p) return GSSD_ERR_ARG;
+    p->det_logits = enable != 0;
+    for (int i = 0; i < p->cfg.C && i < GSSD_MAX_CLASSES; ++i) p->class_bias[i] = (enable && class_bias) ? class_bias[i] : 0.f;
+    return GSSD_OK;
 }
 
 extern "C" int gssd_pipe_set_xchg(gssd_pipe *p, const gssd_xchg *x) {

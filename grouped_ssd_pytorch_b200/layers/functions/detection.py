@@ -13,7 +13,7 @@ from ...config import v2 as cfg
 
 
 def _detect(num_classes, top_k, conf_thresh, nms_thresh, loc_data, conf_data, prior_data, variance,
-            want_aux=False):
+            want_aux=False, logits=False, class_bias=None):
     if nms_thresh <= 0:                                   # detection_pytorch_ver_1point5.py:39-40
         raise ValueError('nms_threshold must be non negative.')
     lib = _lib.require_cuda()
@@ -27,10 +27,22 @@ def _detect(num_classes, top_k, conf_thresh, nms_thresh, loc_data, conf_data, pr
         out = torch.empty((num, num_classes, top_k, 5), dtype=torch.float32, device=dev)
         count = torch.empty((num, num_classes), dtype=torch.int32, device=dev) if want_aux else None
         keep = torch.empty((num, num_classes, top_k), dtype=torch.int32, device=dev) if want_aux else None
-        _lib.check(lib.gssd_detect(loc.data_ptr(), conf.data_ptr(), pri.data_ptr(), num, num_priors, num_classes,
-                                   int(top_k), float(conf_thresh), float(nms_thresh), float(variance[0]),
-                                   float(variance[1]), out.data_ptr(), _lib.ptr(count), _lib.ptr(keep),
-                                   _lib.stream()), "gssd_detect")
+        if logits:
+            import ctypes
+            bias = None
+            if class_bias is not None:
+                if len(class_bias) != num_classes:
+                    raise ValueError("class_bias needs one entry per class")
+                bias = (ctypes.c_float * num_classes)(*[float(v) for v in class_bias])
+            _lib.check(lib.gssd_detect_logits(loc.data_ptr(), conf.data_ptr(), bias, pri.data_ptr(), num, num_priors,
+                                              num_classes, int(top_k), float(conf_thresh), float(nms_thresh),
+                                              float(variance[0]), float(variance[1]), out.data_ptr(), _lib.ptr(count),
+                                              _lib.ptr(keep), _lib.stream()), "gssd_detect_logits")
+        else:
+            _lib.check(lib.gssd_detect(loc.data_ptr(), conf.data_ptr(), pri.data_ptr(), num, num_priors, num_classes,
+                                       int(top_k), float(conf_thresh), float(nms_thresh), float(variance[0]),
+                                       float(variance[1]), out.data_ptr(), _lib.ptr(count), _lib.ptr(keep),
+                                       _lib.stream()), "gssd_detect")
     if not loc_data.is_cuda:
         out = out.cpu()
     return (out, count, keep) if want_aux else out
@@ -67,6 +79,14 @@ class Detect(object):
         with torch.no_grad():
             return _detect(num_classes, top_k, conf_thresh, nms_thresh, loc_data, conf_data, prior_data,
                            cfg['variance'])
+
+    @staticmethod
+    def apply_logits(num_classes, bkg_label, top_k, conf_thresh, nms_thresh, loc_data, conf_logits, prior_data, class_bias=None):
+        """`Detect.apply(..., loc, softmax(conf_logits + class_bias), priors)` in one kernel: the softmax of the model's test
+        phase (ssd_multiphase_custom_group.py:384-390) is evaluated inside the threshold pass (not in the reference API)."""
+        with torch.no_grad():
+            return _detect(num_classes, top_k, conf_thresh, nms_thresh, loc_data, conf_logits, prior_data,
+                           cfg['variance'], logits=True, class_bias=class_bias)
 
     @staticmethod
     def apply_with_indices(num_classes, bkg_label, top_k, conf_thresh, nms_thresh, loc_data, conf_data, prior_data):

@@ -23,13 +23,13 @@ from . import dist as gdist
 class HostBuffers(object):
     """page-locked host memory of one step: loc | conf | scores adjacent (one H2D), losses[2], detections[B,C,top_k,5]"""
 
-    def __init__(self, B, P, Cn, top_k):
+    def __init__(self, B, P, Cn, top_k, with_scores=True):
         a = lambda n: (n + 255) // 256 * 256
         n_loc, n_conf = B * P * 4 * 4, B * P * Cn * 4
-        self.arena = torch.empty((a(n_loc) + a(n_conf) + n_conf,), dtype=torch.uint8).pin_memory()
+        self.arena = torch.empty((a(n_loc) + a(n_conf) + (n_conf if with_scores else 0),), dtype=torch.uint8).pin_memory()
         self.loc = self.arena[:n_loc].view(torch.float32).view(B, P, 4)
         self.conf = self.arena[a(n_loc):a(n_loc) + n_conf].view(torch.float32).view(B, P, Cn)
-        self.scores = self.arena[a(n_loc) + a(n_conf):].view(torch.float32).view(B, P, Cn)
+        self.scores = self.arena[a(n_loc) + a(n_conf):].view(torch.float32).view(B, P, Cn) if with_scores else None
         self.losses = torch.zeros((2,), dtype=torch.float32).pin_memory()
         self.detections = torch.zeros((B, Cn, top_k, 5), dtype=torch.float32).pin_memory()
         self.gt = torch.empty((B * _lib.MAX_GT_PER_IMAGE * 5 + B + 1,), dtype=torch.float32).pin_memory()
@@ -38,7 +38,8 @@ class HostBuffers(object):
 
 class HostPipeline(object):
     def __init__(self, batch, priors, num_classes=2, top_k=200, depth=3, match_thresh=0.5, negpos_ratio=3,
-                 variance=(0.1, 0.2), conf_thresh=0.01, nms_thresh=0.45, max_gt_rows=None, process_group=None, device=None):
+                 variance=(0.1, 0.2), conf_thresh=0.01, nms_thresh=0.45, max_gt_rows=None, process_group=None, device=None,
+                 detect_logits=False, class_bias=None):
         if nms_thresh <= 0:
             raise ValueError('nms_threshold must be non negative.')
         lib = _lib.require_cuda()
@@ -59,6 +60,12 @@ class HostPipeline(object):
             h = C.c_void_p()
             _lib.check(lib.gssd_pipe_create(C.byref(h), C.byref(cfg), self.priors.data_ptr(), self.arena.data_ptr(), nbytes), "gssd_pipe_create")
         self._h, self._lib = h, lib
+        self.detect_logits = bool(detect_logits)
+        if self.detect_logits:                                    # Detect = softmax(conf + class_bias) fused: no scores upload
+            bias = None
+            if class_bias is not None:
+                bias = (C.c_float * self.C)(*[float(v) for v in class_bias])
+            _lib.check(lib.gssd_pipe_set_detect_logits(h, 1, bias), "gssd_pipe_set_detect_logits")
         self.group = process_group
         self._gathered = None
         _, world, _ = gdist.world(process_group)
@@ -67,7 +74,7 @@ class HostPipeline(object):
             _lib.check(lib.gssd_pipe_set_xchg(h, C.byref(self._ex.x)), "gssd_pipe_set_xchg")
 
     def host_buffers(self):
-        return HostBuffers(self.B, self.P, self.C, self.top_k)
+        return HostBuffers(self.B, self.P, self.C, self.top_k, with_scores=not self.detect_logits)
 
     def _pack(self, bufs, targets):
         B = self.B
@@ -91,7 +98,7 @@ class HostPipeline(object):
         """enqueue one step on `bufs` (its loc/conf/scores are read, its losses/detections written); returns the ticket"""
         gt_p, off_p, sum_g, g_max = self._pack(bufs, targets)
         lib, h = self._lib, self._h
-        sc = bufs.scores.data_ptr() if detect else None
+        sc = bufs.scores.data_ptr() if (detect and bufs.scores is not None) else None
         det = bufs.detections.data_ptr() if detect else None
         _, world, _ = gdist.world(self.group)
         if world <= 1 or self._ex is not None:

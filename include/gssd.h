@@ -214,6 +214,14 @@ GSSD_API int gssd_detect(const float *loc, const float *conf, const float *prior
                 int top_k, float conf_thresh, float nms_thresh, float var0, float var1,
                 float *out, int32_t *count, int32_t *keep_idx, void *stream);
 
+/* Detect with the model's softmax fused in (ssd_multiphase_custom_group.py:384-390: `detect(loc, softmax(conf), priors)`):
+ * conf_logits[B,P,C] are the raw head outputs, the class score is softmax(conf_logits + class_bias)[class], evaluated
+ * the way torch's softmax does (row max, exp, sum in class order, IEEE divide).  class_bias_host[C] (host, may be NULL)
+ * is an additive per-class logit offset (prior / calibration shift); everything else as gssd_detect. */
+GSSD_API int gssd_detect_logits(const float *loc, const float *conf_logits, const float *class_bias_host, const float *priors,
+                       int B, int P, int C, int top_k, float conf_thresh, float nms_thresh, float var0, float var1,
+                       float *out, int32_t *count, int32_t *keep_idx, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * L2Norm — replaces L2Norm.forward, layers/modules/l2norm.py:19-23, and its backward.
  *   x[B,Cn,HW] (NCHW), weight[Cn]; y = weight[c] * x / (sqrt(sum_c x^2) + eps)
@@ -327,6 +335,9 @@ GSSD_API int64_t gssd_pipe_begin(gssd_pipe *p, const float *loc_host, const floa
                         float *detect_out_host, void **stream_out);
 GSSD_API int     gssd_pipe_finish(gssd_pipe *p, int64_t ticket, const gssd_loss_stats *global_stats /* device */, int n_global_stats,
                          float *losses_host);
+/* Detect reads the conf logits of the step (softmax fused, gssd_detect_logits) instead of a separate scores tensor:
+ * scores_host of submit/begin is then ignored and may be NULL (25 % fewer H2D bytes at C = 2) */
+GSSD_API int     gssd_pipe_set_detect_logits(gssd_pipe *p, int enable, const float *class_bias_host /* [C] or NULL */);
 /* data-parallel: route the statistics through the peer exchange, so gssd_pipe_submit() serves world_size > 1 too */
 GSSD_API int     gssd_pipe_set_xchg(gssd_pipe *p, const gssd_xchg *x_host);
 /* block until the step's outputs are in the host buffers; its gradients (slot.grad_loc / grad_conf) stay valid until

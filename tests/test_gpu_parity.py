@@ -400,3 +400,22 @@ def test_l2norm_forward_backward():
     w = np.full(512, 20, np.float32)
     m = L2Norm(512, 20).cuda()
     close(m(cu(x)), O.l2norm(x, w))
+
+
+# ---- Detect with the softmax fused in (gssd_detect_logits) -----------------------------------------
+@pytest.mark.parametrize("C,bias", [(2, None), (2, (0.0, -4.0)), (3, (0.5, -2.0, -3.0))])
+def test_detect_from_logits_equals_detect_of_softmax(C, bias):
+    """softmax(conf + bias) evaluated inside the threshold pass must select, order and suppress exactly like
+    Detect(softmax(conf + bias)) with the softmax done by torch on the same device (ssd_multiphase_custom_group.py:384-390)"""
+    from grouped_ssd_pytorch_b200.layers import Detect
+    pri = torch.from_numpy(cases.priors("v2")).cuda()
+    P = pri.shape[0]
+    r = syn.rng(91 + C)
+    loc = torch.from_numpy(syn.loc(r, 3, P, 0.2)).cuda()
+    logits = torch.from_numpy(syn.conf_logits(r, 3, P, C)).cuda()
+    shifted = logits if bias is None else logits + torch.tensor(bias, device="cuda")
+    want = Detect.apply(C, 0, 200, 0.2, 0.45, loc, torch.softmax(shifted, dim=-1), pri)
+    got = Detect.apply_logits(C, 0, 200, 0.2, 0.45, loc, logits, pri, class_bias=bias)
+    assert int((want[..., 0] > 0).sum()) > 50
+    assert torch.equal(got[..., 1:], want[..., 1:]), "kept boxes differ"
+    assert float((got[..., 0] - want[..., 0]).abs().max()) <= 1.2e-7, "scores differ by more than an ulp"
