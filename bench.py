@@ -396,8 +396,16 @@ def run_ours(a):
     if rank == 0:
         hbm, hbm_src = peaks()
         dom = max(kern, key=lambda k: k["us"])
+        traffic = None
+        try:                                                     # dram bytes per launch from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f)
+            if int(tj.get("batch", -1)) == B and a.priors == "v2":
+                traffic = tj.get(dom["name"].split(" ")[0])
+        except Exception:
+            traffic = None
         roof = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["gbs"], "peak": hbm, "unit": "GB/s",
-                "frac": dom["gbs"] / hbm, "traffic": None, "peak_source": hbm_src,
+                "frac": dom["gbs"] / hbm, "traffic": traffic, "peak_source": hbm_src,
                 "algorithmic_bytes_per_launch": dom["bytes"], "avg_launch_us": dom["us"],
                 "kernels": [{k: v for k, v in kk.items()} for kk in kern]}
         line = {
