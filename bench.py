@@ -416,7 +416,8 @@ def run_ours(a):
                        "num_classes": 2, "parallelism": "dp%d (batch-sharded; the 16-byte loss statistics cross ranks as NVLink peer stores from the match kernel)" % world if world > 1 else "dp1",
                        "l2_policy": "ring of %d distinct input sets (%.0f MB) > L2 (126 MB)" % (n_sets, n_sets * per_set / 1e6),
                        "launch": ("cuda-graph replay of the public API calls" if graphs is not None else "eager public API calls") + "; Detect on a second stream beside the loss",
-                       "kernels_per_step": kernels_per_step},
+                       "kernels_per_step": kernels_per_step,
+                       "detect_scores": "softmax(conf + (0,-4)) evaluated inside the Detect kernel (the CPU arm reads the same scores precomputed)"},
             "clocks": clocks,
             "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
