@@ -38,6 +38,7 @@ struct DetShared {
     int n_cand;
     int n_sel;
     int n_keep;
+    int k_final;                       // candidates that enter NMS (read by the helper CTAs of the cluster)
     uint32_t keep_bits[GSSD_MAX_TOP_K / 32];
 };
 
@@ -110,12 +111,19 @@ __device__ __forceinline__ float softmax_class(const float *row, const float *bi
 }
 
 // dynamic smem:  [ u32 keys[n] | (aliased later) u32 mask[top_k][words] ]  u64 ckey[max(k2, CAP)]  float4 box[top_k]  float area[top_k]
-template <bool NMS_MODE>
-__global__ void __launch_bounds__(DET_NT) detect_kernel(DetArgs a) {
+// CL: launched as a cluster (small batches: helper CTAs for the bitmask, one round of loads in the threshold pass, registers
+// unconstrained); !CL: two CTAs per SM for machine-filling batches.
+template <bool NMS_MODE, bool CL>
+__global__ void __launch_bounds__(DET_NT, CL ? 1 : 2) detect_kernel(DetArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ DetShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cl = NMS_MODE ? 0 : blockIdx.x;
+    // Detect mode runs a cluster of S CTAs per (image, class): CTA 0 does the whole job, the others only help with the
+    // suppression bitmask (the one phase that is bound by the issue rate of a single SM) through distributed shared memory
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned S = CL ? cluster.num_blocks() : 1u;
+    const unsigned crank = CL ? cluster.block_rank() : 0u;
+    const int cl = NMS_MODE ? 0 : blockIdx.x / S;
     const int b = NMS_MODE ? 0 : blockIdx.y;
     const int n = a.P;                           // number of scores scanned
     const int top_k = a.top_k;
@@ -131,19 +139,20 @@ __global__ void __launch_bounds__(DET_NT) detect_kernel(DetArgs a) {
     float *out_slab = NMS_MODE ? nullptr : a.out + ((size_t)b * a.C + cl) * top_k * 5;
     int32_t *idx_slab = (NMS_MODE || !a.keep_idx) ? nullptr : a.keep_idx + ((size_t)b * a.C + cl) * top_k;
 
-    if (!NMS_MODE && cl == 0) {                  // background slab stays zero
+    if (!NMS_MODE && cl == 0) {                  // background slab stays zero (the whole cluster leaves: no cluster barrier)
+        if (crank != 0) return;
         for (int i = tid; i < top_k * 5; i += DET_NT) out_slab[i] = 0.f;
         if (idx_slab) for (int i = tid; i < top_k; i += DET_NT) idx_slab[i] = -1;
         if (a.count && tid == 0) a.count[b * a.C] = 0;
         return;
     }
 
-    const bool dbg = blockIdx.x == 1 && blockIdx.y == 0;
+    const bool dbg = cl == 1 && crank == 0 && blockIdx.y == 0;
     GSSD_PHASE(detect, 0, dbg);
     // ---- 1. threshold -> keys, and an optimistic compaction of the candidates -----------------------------
-    if (tid == 0) { sh.n_cand = 0; sh.n_sel = 0; }
+    if (tid == 0) { sh.n_cand = 0; sh.n_sel = 0; sh.k_final = 0; }
     __syncthreads();
-    {
+    if (crank == 0) {
         // append one candidate per lane: warp-aggregated slot allocation
         auto push = [&](bool cand, uint32_t key, int p) {
             const unsigned m = __ballot_sync(FULL, cand);
@@ -154,7 +163,7 @@ __global__ void __launch_bounds__(DET_NT) detect_kernel(DetArgs a) {
                 if (cand && slot < DET_CAND_CAP) ckey[slot] = ((unsigned long long)key << 32) | (unsigned)p;
             }
         };
-        constexpr int U = 4;
+        constexpr int U = CL ? 5 : 4;            // CL, C == 2: 5 float4 = 10 priors per thread -> P <= 10240 in ONE round of loads
         if (!NMS_MODE && a.C == 2 && (n & 1) == 0) {
             // rows are (background, class 1) pairs: one float4 = two priors, the .y / .w lanes are ours
             const float4 *src = reinterpret_cast<const float4 *>(a.conf + (size_t)b * a.P * 2);
@@ -205,11 +214,11 @@ __global__ void __launch_bounds__(DET_NT) detect_kernel(DetArgs a) {
     }
     __syncthreads();
     const int n_cand = sh.n_cand;
-    const int k = min(n_cand, top_k);
-    const int words = (k + 31) / 32;             // 32-candidate blocks actually in use
+    int k = min(n_cand, top_k);
+    int words = (k + 31) / 32;                   // 32-candidate blocks actually in use
 
     GSSD_PHASE(detect, 1, dbg);
-    if (k > 0) {
+    if (crank == 0 && k > 0) {
         // ---- 2. the top_k candidates in descending (score, index) order (box_utils.py:194-196) ---------
         int n2;
         if (n_cand <= DET_CAND_CAP) {            // few candidates: sort them all
@@ -239,13 +248,32 @@ __global__ void __launch_bounds__(DET_NT) detect_kernel(DetArgs a) {
             sbox[i] = bx;
             sarea[i] = box_area(bx);                               // box_utils.py:193
         }
+        if (tid == 0) sh.k_final = k;
         __syncthreads();                                            // keys[] is dead from here: mask aliases it
-        GSSD_PHASE(detect, 5, dbg);
-        // ---- 4. suppression bitmask: bit j of row i (j > i) = box j is removed when i is kept ------------
+    }
+    GSSD_PHASE(detect, 5, dbg);
+    // ---- 4. suppression bitmask: bit j of row i (j > i) = box j is removed when i is kept ----------------
+    // The rows are dealt to the warps of ALL CTAs of the cluster: the helpers copy the boxes out of CTA 0's shared memory
+    // and store their mask words straight into it (distributed shared memory).
+    uint32_t *mask_dst = mask;
+    if (CL && S > 1) {
+        cluster.sync();                                              // CTA 0's boxes are final
+        if (crank != 0) {
+            const DetShared *sh0 = cluster.map_shared_rank(&sh, 0);
+            k = sh0->k_final;
+            words = (k + 31) / 32;
+            const float4 *sbox0 = cluster.map_shared_rank(sbox, 0);
+            const float *sarea0 = cluster.map_shared_rank(sarea, 0);
+            for (int i = tid; i < k; i += DET_NT) { sbox[i] = sbox0[i]; sarea[i] = sarea0[i]; }
+            mask_dst = cluster.map_shared_rank(mask, 0);
+            __syncthreads();
+        }
+    }
+    if (k > 0) {
         // one warp per (row, 32-column word), one IoU per lane, the word is the ballot
         const float thr = a.nms_thresh;
         const float eps = thr * 9.5367431640625e-07f;               // 2^-20 relative: >> the 2-ulp error of the fast divide
-        for (int i = warp; i < k; i += DET_NT / 32) {
+        for (int i = crank * (DET_NT / 32) + warp; i < k; i += S * (DET_NT / 32)) {
             const float4 bi = sbox[i];
             const float ai = sarea[i];
             for (int w = i >> 5; w < words; ++w) {                  // strictly-lower words are never read
@@ -269,11 +297,18 @@ __global__ void __launch_bounds__(DET_NT) detect_kernel(DetArgs a) {
                     else sup = !(__fdiv_rn(inter, uni) <= thr);
                 }
                 const unsigned bits = __ballot_sync(FULL, sup);
-                if (lane == 0) mask[i * words + w] = bits;
+                if (lane == 0) mask_dst[i * words + w] = bits;
             }
         }
+    }
+    if (CL && S > 1) {
+        cluster.sync();                                              // every mask word has landed in CTA 0
+        if (crank != 0) return;
+    } else {
         __syncthreads();
-        GSSD_PHASE(detect, 6, dbg);
+    }
+    GSSD_PHASE(detect, 6, dbg);
+    if (k > 0) {
         // ---- 5. greedy resolve by one warp: lane w owns removed-word w --------------------------------------
         if (warp == 0) {
             uint32_t removed = 0;                                   // word `lane` of the removed set
@@ -349,16 +384,44 @@ static size_t det_smem_bytes(int n, int top_k, int k2) {
 
 static int next_pow2(int v) { int p = 2; while (p < v) p <<= 1; return p; }
 
+template <bool NMS_MODE, bool CL>
+static int launch_detect_as(DetArgs &a, dim3 grid, int S, size_t smem, cudaStream_t st) {
+    auto kern = detect_kernel<NMS_MODE, CL>;
+    GSSD_RETURN_IF_CUDA(allow_max_smem(reinterpret_cast<const void *>(kern)));
+    if (!CL) {
+        kern<<<grid, DET_NT, smem, st>>>(a);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid.x * S, grid.y, 1);
+        cfg.blockDim = dim3(DET_NT, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        GSSD_RETURN_IF_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    }
+    GSSD_AFTER_LAUNCH();
+    return GSSD_OK;
+}
+
 template <bool NMS_MODE>
 static int launch_detect(DetArgs &a, dim3 grid, cudaStream_t st) {
     a.k2 = next_pow2(a.top_k);
     size_t smem = det_smem_bytes(a.P, a.top_k, a.k2);
     if (smem > 227 * 1024) return GSSD_ERR_LIMIT;
-    auto kern = detect_kernel<NMS_MODE>;
-    GSSD_RETURN_IF_CUDA(allow_max_smem(reinterpret_cast<const void *>(kern)));
-    kern<<<grid, DET_NT, smem, st>>>(a);
-    GSSD_AFTER_LAUNCH();
-    return GSSD_OK;
+    // helper CTAs per (image, class) for the bitmask: only while they find idle SMs (small batches)
+    int S = 1;
+    if (!NMS_MODE) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const long active = (long)grid.y * (grid.x > 1 ? grid.x - 1 : 1);    // class 0 leaves at once
+        if (active * 4 <= sms) S = 4; else if (active * 2 <= sms) S = 2;
+    }
+    if (!NMS_MODE && S > 1) return launch_detect_as<NMS_MODE, true>(a, grid, S, smem, st);
+    return launch_detect_as<NMS_MODE, false>(a, grid, 1, smem, st);
 }
 
 }  // namespace gssd

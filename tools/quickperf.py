@@ -44,6 +44,8 @@ def run(pname, B, gmax):
     wsb = lib.gssd_workspace_bytes(_lib.WS_LOSS, B, P, 2, sum_g, 0)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     out = torch.empty(B, 2, 200, 5, device=dev)
+    import ctypes
+    bias = (ctypes.c_float * 2)(0.0, -4.0)
     st = _lib.stream()
 
     def k_match(i):
@@ -53,7 +55,7 @@ def run(pname, B, gmax):
         _lib.check(lib.gssd_mbox_loss(locs[i].data_ptr(), confs[i].data_ptr(), pri.data_ptr(), B, P, 2, gt.data_ptr(), gt_off.data_ptr(), sum_g, g_max, tags.data_ptr(), stats.data_ptr(), None, 0, 3, 0.1, 0.2, losses.data_ptr(), gl[i].data_ptr(), gc[i].data_ptr(), None, None, ws.data_ptr(), wsb, st))
 
     def k_det(i):
-        _lib.check(lib.gssd_detect(locs[i].data_ptr(), scores[i].data_ptr(), pri.data_ptr(), B, P, 2, 200, 0.2, 0.45, 0.1, 0.2, out.data_ptr(), None, None, st))
+        _lib.check(lib.gssd_detect_logits(locs[i].data_ptr(), confs[i].data_ptr(), bias, pri.data_ptr(), B, P, 2, 200, 0.2, 0.45, 0.1, 0.2, out.data_ptr(), None, None, st))
 
     k_match(0)
     tm, tl, td = timeit(k_match, n_sets), timeit(k_loss, n_sets), timeit(k_det, n_sets)
