@@ -426,13 +426,13 @@ def run_ours(a):
             "gpu_launches": int(gpu_launches),
             "roofline": roof,
         }
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and world == 1:                 # the CPU arm is timed on rank 0 at N = 1 only
             from oracle import oracle as O
             priors_np = priors.cpu().numpy()
             done, dt = time_cpu(a, priors_np, host, 10 ** 9, 1, a.cpu_seconds)
             line["cpu_baseline"] = {"value": done * B / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": "%d steps of the batch-%d workload in %.1f s (oracle/gssd_oracle.c, OpenMP over images)" % (done, B, dt)}
-        if not a.no_gconv:
+        if not a.no_gconv and world == 1:
             try:
                 line["gconv"] = time_gconv(a, torch, dev, B)
             except Exception as e:                               # pragma: no cover
