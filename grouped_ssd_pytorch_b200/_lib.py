@@ -109,6 +109,7 @@ _SIGS = {
     "gssd_conv_pack_weights": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "gssd_nchw_to_pm": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "gssd_pm_to_nchw": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "gssd_maxpool_pm": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
     "gssd_bn_act_pm": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _F, _I, _P, _P, _P]),
 }
 

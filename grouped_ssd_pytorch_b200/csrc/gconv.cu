@@ -552,6 +552,45 @@ __global__ void __launch_bounds__(256) bn_act_pm_kernel(__nv_bfloat16 *__restric
     }
 }
 
+// max pooling on PM tensors (nn.MaxPool2d semantics: windows clipped to the image, padding never wins); 8 channels / thread
+__global__ void __launch_bounds__(256) maxpool_pm_kernel(const __nv_bfloat16 *__restrict__ x, int c, int h, int w, int oh, int ow,
+                                                         int k, int stride, int pad, __nv_bfloat16 *__restrict__ y, long total) {
+    const int c8 = c / 8;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int cc = (int)(i % c8);
+        long r = i / c8;
+        const int px = (int)(r % (ow + 2)); r /= (ow + 2);
+        const int py = (int)(r % (oh + 2));
+        const int img = (int)(r / (oh + 2));
+        uint4 out = make_uint4(0, 0, 0, 0);
+        if (py >= 1 && py <= oh && px >= 1 && px <= ow) {
+            float m[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+            const int y0 = (py - 1) * stride - pad, x0 = (px - 1) * stride - pad;
+            for (int ky = 0; ky < k; ++ky) {
+                const int iy = y0 + ky;
+                if (iy < 0 || iy >= h) continue;
+                for (int kx = 0; kx < k; ++kx) {
+                    const int ix = x0 + kx;
+                    if (ix < 0 || ix >= w) continue;
+                    const uint4 v = *reinterpret_cast<const uint4 *>(x + (((size_t)img * (h + 2) + iy + 1) * (w + 2) + ix + 1) * c + cc * 8);
+                    const uint32_t *vw = reinterpret_cast<const uint32_t *>(&v);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162 *>(&vw[j]);
+                        m[2 * j] = fmaxf(m[2 * j], __low2float(b2));
+                        m[2 * j + 1] = fmaxf(m[2 * j + 1], __high2float(b2));
+                    }
+                }
+            }
+            out.x = tc::pack_bf16x2(m[0], m[1]); out.y = tc::pack_bf16x2(m[2], m[3]);
+            out.z = tc::pack_bf16x2(m[4], m[5]); out.w = tc::pack_bf16x2(m[6], m[7]);
+        }
+        *reinterpret_cast<uint4 *>(y + i * 8) = out;
+    }
+}
+
 __global__ void bn_mean_var_kernel(const float *__restrict__ chan_sum, int c, float inv_count, float unbias, float *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < c) {
@@ -707,5 +746,28 @@ extern "C" int gssd_bn_act_pm(void *y_bf16, int n_img, int c, int h, int w, cons
                                                                               (float)(count > 1 ? count / (count - 1) : 1.0), mean_var_out);
         GSSD_AFTER_LAUNCH();
     }
+    return GSSD_OK;
+}
+
+extern "C" int gssd_maxpool_pm(const void *x_bf16, int n_img, int c, int h, int w, int kernel, int stride, int pad, int ceil_mode,
+                               void *y_bf16, int *out_h, int *out_w, void *stream) {
+    if (n_img <= 0 || c <= 0 || h <= 0 || w <= 0 || kernel <= 0 || stride <= 0 || pad < 0 || 2 * pad > kernel) return GSSD_ERR_ARG;
+    if (c % 8) return GSSD_ERR_LIMIT;
+    auto osz = [&](int in) {                                                   // nn.MaxPool2d output size
+        const int num = in + 2 * pad - kernel;
+        int o = (ceil_mode ? (num + stride - 1) / stride : num / stride) + 1;
+        if (ceil_mode && (o - 1) * stride >= in + pad) --o;                    // the last window must start inside the input
+        return o;
+    };
+    const int oh = osz(h), ow = osz(w);
+    if (out_h) *out_h = oh;
+    if (out_w) *out_w = ow;
+    if (oh <= 0 || ow <= 0) return GSSD_ERR_ARG;
+    if (x_bf16 == nullptr || y_bf16 == nullptr) return (x_bf16 == nullptr && y_bf16 == nullptr) ? GSSD_OK : GSSD_ERR_ARG;   // size query
+    const long total = (long)n_img * (oh + 2) * (ow + 2) * (c / 8);
+    const int blocks = (int)((total + 255) / 256 < 148l * 16 ? (total + 255) / 256 : 148l * 16);
+    maxpool_pm_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16 *>(x_bf16), c, h, w, oh, ow, kernel,
+                                                                 stride, pad, reinterpret_cast<__nv_bfloat16 *>(y_bf16), total);
+    GSSD_AFTER_LAUNCH();
     return GSSD_OK;
 }

@@ -54,6 +54,84 @@ class PM(object):
         return y
 
 
+def maxpool_pm(x, pool):
+    """nn.MaxPool2d on a PM tensor (gssd_maxpool_pm)."""
+    lib = _lib.require_cuda()
+    one = lambda v: v if isinstance(v, int) else v[0]
+    k, st, pd = one(pool.kernel_size), one(pool.stride), one(pool.padding)
+    if one(pool.dilation) != 1:
+        raise NotImplementedError("dilated pooling")
+    oh, ow = C.c_int(), C.c_int()
+    _lib.check(lib.gssd_maxpool_pm(None, x.n, x.c, x.h, x.w, k, st, pd, int(bool(pool.ceil_mode)), None, C.byref(oh), C.byref(ow), None))
+    out = PM.empty(x.n, x.c, oh.value, ow.value, x.data.device)
+    with torch.cuda.device(x.data.device):
+        _lib.check(lib.gssd_maxpool_pm(x.data.data_ptr(), x.n, x.c, x.h, x.w, k, st, pd, int(bool(pool.ceil_mode)),
+                                       out.data.data_ptr(), None, None, _lib.stream()), "gssd_maxpool_pm")
+    return out
+
+
+def _conv_eligible(conv):
+    """stride-1 1x1 / 3x3 'same' convolutions whose per-group channel counts are multiples of 64 run on gssd_conv_igemm"""
+    import torch.nn as nn
+    if not isinstance(conv, nn.Conv2d):
+        return False
+    kh, kw = conv.kernel_size
+    return ((kh, kw) in ((1, 1), (3, 3)) and conv.stride == (1, 1) and conv.dilation == (1, 1)
+            and conv.padding == ((kh - 1) // 2, (kw - 1) // 2)
+            and (conv.in_channels // conv.groups) % 64 == 0 and (conv.out_channels // conv.groups) % 64 == 0)
+
+
+class BackboneRun(object):
+    """A stretch of the model's `vgg` ModuleList executed in PM/bf16: every [Conv2d, (BatchNorm2d), ReLU] triple whose
+    conv fits the tcgen05 kernel runs as one launch with BN folded and ReLU fused (eval mode), MaxPool2d runs on PM, and
+    anything else (conv6: dilation 6) round-trips through torch.  SURVEY §8f rank 1, forward half."""
+
+    def __init__(self, modules):
+        self.modules = list(modules)
+        self._packed = {}
+
+    def _conv(self, i, conv, bn, dev):
+        key = (_versions(conv, bn), str(dev))
+        hit = self._packed.get(i)
+        if hit is None or hit[0] != key:
+            with torch.no_grad(), torch.cuda.device(dev):
+                cv = _Conv(conv, conv.groups, dev=dev)
+                if bn is not None:
+                    cv.fold_bn(bn)
+            hit = (key, cv)
+            self._packed[i] = hit
+        return hit[1]
+
+    def __call__(self, x, start, stop):
+        """x: PM or NCHW tensor; runs modules[start:stop]; returns PM"""
+        import torch.nn as nn
+        mods = self.modules
+        i = start
+        while i < stop:
+            m = mods[i]
+            nxt = mods[i + 1] if i + 1 < stop else None
+            if _conv_eligible(m):
+                bn = nxt if isinstance(nxt, nn.BatchNorm2d) else None
+                j = i + (2 if bn is not None else 1)
+                relu = j < stop and isinstance(mods[j], nn.ReLU)
+                if bn is not None and bn.training:
+                    raise NotImplementedError("BackboneRun folds BatchNorm: eval mode only")
+                if not isinstance(x, PM):
+                    x = PM.from_nchw(x)
+                cv = self._conv(i, m, bn, x.data.device)
+                x = conv_igemm(x, cv, relu=relu, scale=cv.scale, shift=cv.shift)
+                i = j + (1 if relu else 0)
+            elif isinstance(m, nn.MaxPool2d) and isinstance(x, PM):
+                x = maxpool_pm(x, m)
+                i += 1
+            else:
+                if isinstance(x, PM):
+                    x = x.to_nchw()
+                x = m(x)
+                i += 1
+        return x if isinstance(x, PM) else PM.from_nchw(x)
+
+
 def _versions(*mods):
     v = []
     for m in mods:
@@ -235,7 +313,7 @@ def build_source_blocks(net):
     return blocks, (i43, i7)
 
 
-def gssd_forward(net, x, detect_args=(0, 200, 0.01, 0.45)):
+def gssd_forward(net, x, detect_args=(0, 200, 0.01, 0.45), backbone=False):
     """Forward of the reference's SSD (ssd_multiphase_custom_group.py:217-400, ssd_type gssd) with every source chain
     — grouped conv / BN / ReLU / L2Norm / fuse 1x1 / BN / ReLU / loc+conf heads / permute / flatten / concat — run by
     the tcgen05 source blocks; the rest of the backbone stays the model's own torch modules.  Forward only
@@ -243,6 +321,10 @@ def gssd_forward(net, x, detect_args=(0, 200, 0.01, 0.45)):
     `Detect` output `[B,C,top_k,5]` in the test phase (ssd_multiphase_custom_group.py:382-396).
 
         net.forward = types.MethodType(gssd_forward, net)        # drop-in
+
+    backbone=True (opt-in, eval mode) also runs every grouped backbone conv the kernel takes — conv3_2 .. conv5_3, with
+    BatchNorm folded, ReLU fused and the pools on the PM layout — in bf16: 1.5x the model's fp32 torch forward at batch 32,
+    at 1.0e-2 / 6.6e-3 relative error on loc / conf instead of 6.0e-3 / 3.7e-3 (tests/test_gpu_model.py).
     """
     import torch.nn.functional as F
     from ..functions import Detect
@@ -260,15 +342,31 @@ def gssd_forward(net, x, detect_args=(0, 200, 0.01, 0.45)):
         loc = torch.empty((B, P, 4), dtype=torch.float32, device=x.device)
         conf = torch.empty((B, P, net.num_classes), dtype=torch.float32, device=x.device)
         off = 0
-        for k in range(i43):                                     # GSSD:254-259, up to the input of conv4_3
-            x = net.vgg[k](x)
-        x1, n = blocks[0](x, loc, conf, off)                     # conv4_3 .. heads of source 1 (GSSD:258-297, 375-377)
-        off += n
-        x = x1.to_nchw()                                         # post-ReLU conv4_3 continues down the backbone
-        for k in range(i43 + (3 if bn else 2), i7):              # GSSD:300-301 up to the input of conv7
-            x = net.vgg[k](x)
-        x2, n = blocks[1](x, loc, conf, off)                     # conv7 .. heads of source 2 (GSSD:300-325)
-        off += n
+        if backbone and not net.training:
+            # every grouped backbone conv the tcgen05 kernel takes (conv3_2 .. conv5_3) stays in PM/bf16 with BN folded
+            run = getattr(net, "_gssd_backbone", None)
+            if run is None:
+                run = BackboneRun(net.vgg)
+                net._gssd_backbone = run
+            first = next((k for k in range(i43) if _conv_eligible(net.vgg[k])), i43)
+            for k in range(first):                               # GSSD:254-259: the layers in front stay torch
+                x = net.vgg[k](x)
+            x = run(x, first, i43)
+            x1, n = blocks[0](x, loc, conf, off)                 # conv4_3 .. heads of source 1 (GSSD:258-297, 375-377)
+            off += n
+            x = run(x1, i43 + (3 if bn else 2), i7)              # GSSD:300-301 up to the input of conv7
+            x2, n = blocks[1](x, loc, conf, off)                 # conv7 .. heads of source 2 (GSSD:300-325)
+            off += n
+        else:
+            for k in range(i43):                                 # GSSD:254-259, up to the input of conv4_3
+                x = net.vgg[k](x)
+            x1, n = blocks[0](x, loc, conf, off)                 # conv4_3 .. heads of source 1 (GSSD:258-297, 375-377)
+            off += n
+            x = x1.to_nchw()                                     # post-ReLU conv4_3 continues down the backbone
+            for k in range(i43 + (3 if bn else 2), i7):          # GSSD:300-301 up to the input of conv7
+                x = net.vgg[k](x)
+            x2, n = blocks[1](x, loc, conf, off)                 # conv7 .. heads of source 2 (GSSD:300-325)
+            off += n
         x = x2.to_nchw()
         si = 2
         for k, v in enumerate(net.extras):                       # GSSD:329-372

@@ -284,6 +284,11 @@ GSSD_API int gssd_conv_pack_weights(const float *w, int c_out, int c_in_per_grou
 /* layout converters between torch's NCHW fp32 and PM bf16 (borders written as zeros) */
 GSSD_API int gssd_nchw_to_pm(const float *x, int n_img, int c, int h, int w, void *y_bf16, void *stream);
 GSSD_API int gssd_pm_to_nchw(const void *x_bf16, int n_img, int c, int h, int w, float *y, void *stream);
+/* nn.MaxPool2d on a PM tensor (the pools between the grouped backbone convs, ssd_multiphase_custom_group.py:437-446):
+ * y PM [n_img, out_h, out_w, c]; out_h / out_w (host, optional) receive the output extent; with x == y == NULL the call
+ * only computes them. */
+GSSD_API int gssd_maxpool_pm(const void *x_bf16, int n_img, int c, int h, int w, int kernel, int stride, int pad, int ceil_mode,
+                    void *y_bf16, int *out_h_host, int *out_w_host, void *stream);
 /* train-mode BatchNorm (+ReLU) applied in place on a PM tensor from the statistics a conv call left in
  * chan_sum (biased variance, as F.batch_norm normalises): y = relu?((y - mean)*rstd*gamma + beta) on interior
  * pixels; row_ss_out (optional) receives sum_c y^2 per pixel; mean_var_out[2*c] (optional) the batch mean and
