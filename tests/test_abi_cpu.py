@@ -84,6 +84,43 @@ def test_argument_errors_are_reported_before_any_launch():
         _lib.check(_lib.ERR_WS)
 
 
+def test_source_block_and_pipeline_argument_errors():
+    """the tcgen05 conv, the PM helpers, the exchange and the pipeline validate their arguments on the host"""
+    import ctypes as C
+    lib = _lib.load()
+    d = _lib.ConvDesc()
+    assert lib.gssd_conv_igemm(C.byref(d), None) == _lib.ERR_ARG                       # null tensors
+    d.x, d.w, d.y = 1, 1, 1
+    d.n_img, d.height, d.width, d.c_in, d.c_out, d.groups, d.taps = 1, 4, 4, 96, 128, 1, 9
+    assert lib.gssd_conv_igemm(C.byref(d), None) == _lib.ERR_LIMIT                     # c_in/groups must be a multiple of 64
+    d.c_in, d.taps = 128, 5
+    assert lib.gssd_conv_igemm(C.byref(d), None) == _lib.ERR_ARG                       # only 1x1 and 3x3
+    d.taps, d.c_out = 9, 100
+    assert lib.gssd_conv_igemm(C.byref(d), None) == _lib.ERR_LIMIT                     # c_out/groups must be a multiple of 64
+    d.c_out, d.width = 128, 3000
+    assert lib.gssd_conv_igemm(C.byref(d), None) == _lib.ERR_LIMIT                     # slab of a 3000-wide map does not fit
+    d.width, d.y, d.loc, d.conf, d.n_anchor, d.n_cls, d.n_priors, d.c_out = 4, None, 1, 1, 4, 2, 64, 20
+    assert lib.gssd_conv_igemm(C.byref(d), None) == _lib.ERR_ARG                       # head: c_out must be anchors * (4 + classes)
+    assert lib.gssd_conv_pack_weights(1, 64, 64, 1, 4, None, 1, None) == _lib.ERR_ARG
+    assert lib.gssd_nchw_to_pm(None, 1, 64, 4, 4, None, None) == _lib.ERR_ARG
+    oh, ow = C.c_int(), C.c_int()
+    assert lib.gssd_maxpool_pm(None, 1, 64, 75, 75, 2, 2, 0, 1, None, C.byref(oh), C.byref(ow), None) == 0 and (oh.value, ow.value) == (38, 38)
+    assert lib.gssd_maxpool_pm(None, 1, 64, 19, 19, 3, 1, 1, 0, None, C.byref(oh), C.byref(ow), None) == 0 and (oh.value, ow.value) == (19, 19)
+    assert lib.gssd_maxpool_pm(None, 1, 60, 19, 19, 3, 1, 1, 0, None, None, None, None) == _lib.ERR_LIMIT
+    cfg = _lib.PipeCfg()
+    assert lib.gssd_pipe_arena_bytes(C.byref(cfg)) == 0
+    cfg.B, cfg.P, cfg.C, cfg.top_k, cfg.max_gt_rows, cfg.depth = 2, 158, 2, 200, 64, 3
+    cfg.var0, cfg.var1, cfg.nms_thresh = 0.1, 0.2, 0.45
+    assert lib.gssd_pipe_arena_bytes(C.byref(cfg)) > 2 * 158 * (16 + 8 + 8 + 16 + 8) * 3
+    h = C.c_void_p()
+    assert lib.gssd_pipe_create(C.byref(h), C.byref(cfg), None, None, 0) == _lib.ERR_ARG
+    cfg.nms_thresh = 0.0
+    assert lib.gssd_pipe_create(C.byref(h), C.byref(cfg), 1, 1, 1 << 30) == _lib.ERR_VALUE   # detection_pytorch_ver_1point5.py:39-40
+    x = _lib.Xchg()
+    assert lib.gssd_mbox_match_x(1, 100, None, 2, 1, 1, 2, 4, 2, 0.5, 1, 1, C.byref(x), None) == _lib.ERR_ARG   # world == 0
+    assert lib.gssd_detect_logits(1, 1, None, 1, 1, 10, 1, 200, 0.1, 0.45, 0.1, 0.2, 1, None, None, None) == _lib.ERR_ARG   # softmax needs C >= 2
+
+
 def test_layers_module_tree_mirrors_the_reference():
     from grouped_ssd_pytorch_b200 import layers
     from grouped_ssd_pytorch_b200.layers import Detect, L2Norm, MultiBoxLoss, PriorBox, box_utils
