@@ -15,6 +15,8 @@
 //   warps 4-11  epilogue: tcgen05.ld (thread = row, 32 columns at a time) -> scale/shift/ReLU/L2Norm/BN-statistics ->
 //               bf16 PM tile through a TMA store, or fp32 scatter into loc/conf (head mode)
 // DESIGN.md section 4b has the measurements behind each choice.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -74,7 +76,10 @@ __global__ void __launch_bounds__(384, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ CUtensorMap map_y, const ConvParams p) {
     constexpr int B_BYTES = BN * 128;
-    constexpr int TMEM_COLS = (2 * MSUB * BN) < 32 ? 32 : 2 * MSUB * BN;     // two units in flight
+    // accumulator stages: two units in flight (the epilogue of one overlaps the MMAs of the next) unless a unit alone fills
+    // the 512 TMEM columns (BN = 256 with two sub-tiles: half the weight traffic per output row, epilogue not overlapped)
+    constexpr int ACC = (2 * MSUB * BN <= 512) ? 2 : 1;
+    constexpr int TMEM_COLS = (ACC * MSUB * BN) < 32 ? 32 : ACC * MSUB * BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int slab_bytes = p.a_nbox * p.a_box_rows * 128;
@@ -184,8 +189,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             // rate with 8 MMAs per wait/commit, 80% with 24).  One wait + one commit therefore cover a whole B stage:
             // the 3 taps of a filter row (24 MMAs at MSUB = 2) or kg chunks of a 1x1.
             for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
-                const uint32_t acc = it & 1;
-                TWAIT(w_te, tc::mbar_wait(&bar_tempty[acc], ((it >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator
+                const uint32_t acc = it % ACC;
+                TWAIT(w_te, tc::mbar_wait(&bar_tempty[acc], ((it / ACC) & 1) ^ 1));   // the epilogue has drained this accumulator
                 tc::fence_after_thread_sync();
                 const uint32_t tmem_d0 = tmem_base + acc * MSUB * BN;
                 for (int cc = 0; cc < k_per_tap; cc += kg) {
@@ -249,11 +254,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         uint32_t it = 0, n_store = 0;
         long long w_tf = 0, w_ld = 0, w_sg = 0, t_start = clock64();
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
-            const uint32_t acc = it & 1;
+            const uint32_t acc = it % ACC;
             const int mt = unit / units, u = unit - mt * units;
             const int g = u / nt_per_group, nt = u - g * nt_per_group;
             const int col_base = g * ng + nt * BN;
-            TWAIT(w_tf, tc::mbar_wait(&bar_tfull[acc], (it >> 1) & 1));
+            TWAIT(w_tf, tc::mbar_wait(&bar_tfull[acc], (it / ACC) & 1));
             tc::fence_after_thread_sync();
             int cur_sub = -1, m = 0, m_warp = 0;
             bool interior = false;
@@ -643,7 +648,10 @@ extern "C" int gssd_conv_igemm(const gssd_conv_desc *d, void *stream) {
     p.loc = d->loc; p.conf = d->conf; p.n_anchor = d->n_anchor; p.n_cls = d->n_cls; p.prior_off = d->prior_off; p.n_priors = d->n_priors;
 
     // ---- tile geometry ----
-    const int msub = (bn <= 128 && !head) ? 2 : 1;                             // heads: tiny weight tiles, nothing to share
+    // two 128-row sub-tiles share every weight tile (heads: tiny weight tiles, nothing to share).  At BN = 256 a pair would
+    // fill all 512 TMEM columns and serialise the epilogue behind the MMAs: measured slower (fuse_11 50 us against 38 us),
+    // although it halves the weight bytes per output row
+    const int msub = (bn <= 128 && !head) ? 2 : 1;
     const int tile_rows = 128 * msub;
     p.halo = d->taps == 9 ? p.wp + 1 : 0;
     const int slab_rows = tile_rows + 2 * p.halo;
