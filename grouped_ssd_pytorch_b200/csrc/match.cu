@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
     __shared__ float s_warp_max[MATCH_NT / 32];
     __shared__ float s_bbox[4][MATCH_NT / 32];
     __shared__ int s_nlist;
+    __shared__ bool s_is_last;
 
     const int p0 = rank * a.slice;
     const int p1 = min(a.P, p0 + a.slice);
@@ -268,23 +269,28 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
                 // the LAST CTA of the grid publishes this rank's statistics into every peer's exchange buffer
                 XBuf *xl = a.x.peers[a.x.rank];
                 __threadfence();
-                const unsigned done = atomicAdd(&xl->match_done, 1u);
-                if (done == gridDim.x * gridDim.y - 1) {
-                    __threadfence();
-                    const uint32_t mo = atomicMax(&a.stats[0], 0u);
-                    const int np = atomicAdd(reinterpret_cast<int *>(&a.stats[1]), 0);
-                    const uint32_t e = xl->epoch + 1;
-                    xl->match_done = 0;
-                    for (int r = 0; r < a.x.world; ++r) {
-                        XSlot *dst = &a.x.peers[r]->slot[e & 1][a.x.rank];
-                        dst->conf_max_ord = mo; dst->num_pos = np;
-                    }
-                    __threadfence_system();                               // data before the epoch tags, system scope
-                    for (int r = 0; r < a.x.world; ++r)
-                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&a.x.peers[r]->slot[e & 1][a.x.rank].epoch), "r"(e) : "memory");
-                    xl->epoch = e;
-                }
+                s_is_last = atomicAdd(&xl->match_done, 1u) == gridDim.x * gridDim.y - 1;
             }
+        }
+    }
+    if (a.x.world > 0) {
+        __syncthreads();
+        if (s_is_last && warp == 0) {
+            // one lane per peer: statistics, one system-scope fence, then the epoch tag — the peers' stage 2 polls the tag
+            XBuf *xl = a.x.peers[a.x.rank];
+            __threadfence();
+            const uint32_t mo = atomicMax(&a.stats[0], 0u);
+            const int np = atomicAdd(reinterpret_cast<int *>(&a.stats[1]), 0);
+            const uint32_t e = *reinterpret_cast<volatile uint32_t *>(&xl->epoch) + 1;
+            if (lane < a.x.world) {
+                XSlot *dst = &a.x.peers[lane]->slot[e & 1][a.x.rank];
+                *reinterpret_cast<volatile uint32_t *>(&dst->conf_max_ord) = mo;
+                *reinterpret_cast<volatile int32_t *>(&dst->num_pos) = np;
+                __threadfence_system();                                   // data before the tag, visible to the peer GPU
+                *reinterpret_cast<volatile uint32_t *>(&dst->epoch) = e;
+            }
+            __syncwarp();
+            if (lane == 0) { xl->match_done = 0; *reinterpret_cast<volatile uint32_t *>(&xl->epoch) = e; }
         }
     }
     GSSD_PHASE(match, 3, dbg);
