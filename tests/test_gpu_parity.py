@@ -419,3 +419,22 @@ def test_detect_from_logits_equals_detect_of_softmax(C, bias):
     assert int((want[..., 0] > 0).sum()) > 50
     assert torch.equal(got[..., 1:], want[..., 1:]), "kept boxes differ"
     assert float((got[..., 0] - want[..., 0]).abs().max()) <= 1.2e-7, "scores differ by more than an ulp"
+
+
+def test_collect_detections_mirrors_the_evaluator_loop():
+    """test_ap_iobb.py:124-149 restated per image with numpy vs the batched device-side collect_detections"""
+    from grouped_ssd_pytorch_b200.layers.functions import collect_detections
+    loc, conf, pri, C, thr = cases.detect_case("a")
+    out = Detect.apply(C, 0, 200, thr, 0.45, torch.from_numpy(loc).cuda(), torch.from_numpy(conf).cuda(), torch.from_numpy(pri).cuda())
+    W, H, cut = 512.0, 384.0, 0.3
+    got = collect_detections(out, W, H, cut)
+    want = []
+    o = out.cpu().numpy()
+    for idx in range(o.shape[0]):
+        det = o[idx, 1]
+        det = det[det[:, 0] > 0]
+        boxes = np.hstack([np.full((det.shape[0], 1), idx, np.float32), det[:, :1], det[:, 1:] * np.array([W, H, W, H], np.float32)])
+        want.append(boxes[boxes[:, 1] > cut])
+    want = np.concatenate(want, 0).astype(np.float32)
+    assert got.shape == want.shape and got.shape[0] > 10
+    np.testing.assert_array_equal(got, want)
