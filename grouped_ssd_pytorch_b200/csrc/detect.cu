@@ -152,7 +152,10 @@ __global__ void __launch_bounds__(DET_NT, CL ? 1 : 2) detect_kernel(DetArgs a) {
     // ---- 1. threshold -> keys, and an optimistic compaction of the candidates -----------------------------
     if (tid == 0) { sh.n_cand = 0; sh.n_sel = 0; sh.k_final = 0; }
     __syncthreads();
-    if (crank == 0) {
+    // C == 2 in a cluster: every CTA scans its own slice of the priors into its own (keys, candidate list); CTA 0 then pulls
+    // the helpers' candidates (and, if there are too many for the direct sort, their keys) through distributed shared memory
+    const bool split_scan = CL && S > 1 && !NMS_MODE && a.C == 2 && (n & 1) == 0;
+    if (crank == 0 || split_scan) {
         // append one candidate per lane: warp-aggregated slot allocation
         auto push = [&](bool cand, uint32_t key, int p) {
             const unsigned m = __ballot_sync(FULL, cand);
@@ -163,17 +166,19 @@ __global__ void __launch_bounds__(DET_NT, CL ? 1 : 2) detect_kernel(DetArgs a) {
                 if (cand && slot < DET_CAND_CAP) ckey[slot] = ((unsigned long long)key << 32) | (unsigned)p;
             }
         };
-        constexpr int U = CL ? 5 : 4;            // CL, C == 2: 5 float4 = 10 priors per thread -> P <= 10240 in ONE round of loads
+        constexpr int U = CL ? 2 : 4;            // loads in flight per thread (a cluster CTA owns about one float4 per thread)
         if (!NMS_MODE && a.C == 2 && (n & 1) == 0) {
             // rows are (background, class 1) pairs: one float4 = two priors, the .y / .w lanes are ours
             const float4 *src = reinterpret_cast<const float4 *>(a.conf + (size_t)b * a.P * 2);
             const int n4 = n >> 1;
-            for (int base = 0; base < n4; base += DET_NT * U) {
+            const int per = split_scan ? (n4 + (int)S - 1) / (int)S : n4;
+            const int q_lo = split_scan ? (int)crank * per : 0, q_hi = min(n4, q_lo + per);
+            for (int base = q_lo; base < q_hi; base += DET_NT * U) {
                 float4 sv[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int q = base + u * DET_NT + tid;
-                    sv[u] = q < n4 ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    sv[u] = q < q_hi ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
                     if (a.logits) {                                         // fused softmax: (.y, .w) become the class-1 scores
                         sv[u].y = softmax2_class1(__fadd_rn(sv[u].x, a.bias[0]), __fadd_rn(sv[u].y, a.bias[1]));
                         sv[u].w = softmax2_class1(__fadd_rn(sv[u].z, a.bias[0]), __fadd_rn(sv[u].w, a.bias[1]));
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(DET_NT, CL ? 1 : 2) detect_kernel(DetArgs a) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int q = base + u * DET_NT + tid;
-                    const bool ok = q < n4;
+                    const bool ok = q < q_hi;
                     const bool c0 = ok && sv[u].y > a.conf_thresh, c1 = ok && sv[u].w > a.conf_thresh;   // strict >, line 69
                     const uint32_t k0 = c0 ? f2ord(sv[u].y) : 0u, k1 = c1 ? f2ord(sv[u].w) : 0u;
                     if (ok) *reinterpret_cast<uint2 *>(keys + 2 * q) = make_uint2(k0, k1);
@@ -210,6 +215,36 @@ __global__ void __launch_bounds__(DET_NT, CL ? 1 : 2) detect_kernel(DetArgs a) {
                     push(cand, key, p);
                 }
             }
+        }
+    }
+    if (split_scan) {
+        cluster.sync();                                              // every CTA's slice is scanned
+        if (crank == 0) {
+            int cnt[8];
+            int total = 0;
+            bool overflow = false;
+            for (unsigned r = 0; r < S; ++r) {
+                cnt[r] = r == 0 ? sh.n_cand : cluster.map_shared_rank(&sh, r)->n_cand;
+                overflow |= cnt[r] > DET_CAND_CAP;
+                total += cnt[r];
+            }
+            __syncthreads();                                         // everyone has read sh.n_cand before it is replaced
+            if (total <= DET_CAND_CAP && !overflow) {                // the usual case: append the helpers' candidates
+                int off = cnt[0];
+                for (unsigned r = 1; r < S; ++r) {
+                    const unsigned long long *src = cluster.map_shared_rank(ckey, r);
+                    for (int i = tid; i < cnt[r]; i += DET_NT) ckey[off + i] = src[i];
+                    off += cnt[r];
+                }
+            } else {                                                 // too many for the direct sort: the select needs every key
+                const int n4 = n >> 1, per = (n4 + (int)S - 1) / (int)S;
+                for (unsigned r = 1; r < S; ++r) {
+                    const uint32_t *src = cluster.map_shared_rank(keys, r);
+                    const int lo = 2 * min(n4, (int)r * per), hi = 2 * min(n4, ((int)r + 1) * per);
+                    for (int i = lo + tid; i < hi; i += DET_NT) keys[i] = src[i];
+                }
+            }
+            if (tid == 0) sh.n_cand = total;
         }
     }
     __syncthreads();
