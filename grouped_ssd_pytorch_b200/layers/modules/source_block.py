@@ -329,6 +329,11 @@ def gssd_forward(net, x, detect_args=(0, 200, 0.01, 0.45), backbone=False):
     import torch.nn.functional as F
     from ..functions import Detect
     _lib.require_cuda()
+    if net.training and torch.is_grad_enabled() and not getattr(net, "_gssd_warned", False):
+        import warnings
+        warnings.warn("gssd_forward is forward-only: no autograd graph is recorded through the source blocks "
+                      "(train-mode BatchNorm statistics are still updated)")
+        net._gssd_warned = True
     cache = getattr(net, "_gssd_blocks", None)
     if cache is None:
         cache = build_source_blocks(net)
