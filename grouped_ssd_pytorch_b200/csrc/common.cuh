@@ -60,20 +60,22 @@ static inline cudaError_t allow_max_smem(const void *kern) {
     return cudaSuccess;
 }
 
-// Cluster size (CTAs per image, 1/2/4/8) for the per-image kernels: enough CTAs to fill the machine, and a
-// CTA count that packs into whole waves (`slots` = resident CTAs of the kernel on the device), with a fixed
-// cost per CTA (`fixed`, in priors) for staging, cluster barriers and the tail of each phase.
-static inline int pick_cluster_size(int B, int P, int slots, int fixed) {
-    int best_s = 1;
-    double best_cost = 1e300;
-    for (int s = 1; s <= 8; s *= 2) {
-        if (s > 1 && P / s < 512) break;
-        const long ctas = (long)B * s;
-        const long waves = (ctas + slots - 1) / slots;
-        const double cost = (double)waves * ((double)(P + s - 1) / s + fixed + (s > 1 ? fixed : 0));
-        if (cost < best_cost * 0.97) { best_cost = cost; best_s = s; }
-    }
-    return best_s;
+// Cluster size (CTAs per image, 1/2/4/8) for the per-image kernels.  Measured on B200 (tools/quickperf.py with every size
+// forced, profiles/r1_cluster_sizes.txt): while the batch alone cannot fill the machine (8 CTAs per image still fit 4 CTAs per
+// SM) the widest cluster wins by a factor of two; beyond that the cluster barriers cost more than the parallelism returns and
+// the size only has to keep enough warps resident — the loss kernel's per-image key array (4 bytes per prior of the slice)
+// limits the CTAs per SM at SSD512 prior counts, so it keeps 4 CTAs per image there.
+enum { GSSD_KERNEL_MATCH = 0, GSSD_KERNEL_LOSS = 1 };
+static inline int pick_cluster_size(int kernel, int B, int P) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int S;
+    if ((long)B * 8 <= 4l * sms) S = 8;                            // B <= 74 on B200
+    else if (kernel == GSSD_KERNEL_LOSS) S = P >= 16384 ? 4 : (B <= 512 ? 2 : 1);
+    else S = 2;
+    while (S > 1 && P / S < 512) S >>= 1;                          // tiny prior sets: nothing to split
+    return S;
 }
 
 static inline int resident_ctas(const void *kern, int threads, size_t smem) {

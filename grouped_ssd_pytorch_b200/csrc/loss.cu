@@ -263,8 +263,7 @@ static int launch_loss(LossArgs &a, int g_max, cudaStream_t stream) {
     // the cluster-capable instantiation also runs as a 1-CTA "cluster"; pick the size from its occupancy
     auto kern_cl = loss_kernel<C2, true, GR>;
     GSSD_RETURN_IF_CUDA(allow_max_smem(reinterpret_cast<const void *>(kern_cl)));
-    const int slots = resident_ctas(reinterpret_cast<const void *>(kern_cl), LOSS_NT, loss_smem_bytes(g_max, ceil_div(a.P, 4)));
-    const int S = pick_cluster_size(a.B, a.P, slots, 384);
+    const int S = pick_cluster_size(GSSD_KERNEL_LOSS, a.B, a.P);
     a.slice = ceil_div(a.P, S);
     auto kern = S > 1 ? kern_cl : loss_kernel<C2, false, GR>;
     size_t smem = loss_smem_bytes(g_max, a.slice);

@@ -303,8 +303,7 @@ static int launch_match(const MatchArgs &a_in, int B, int g_max, cudaStream_t st
     MatchArgs a = a_in;
     auto kern = match_kernel<MAT, CMAX>;
     GSSD_RETURN_IF_CUDA(allow_max_smem(reinterpret_cast<const void *>(kern)));
-    const int slots = resident_ctas(reinterpret_cast<const void *>(kern), MATCH_NT, match_smem_bytes(g_max, ceil_div(a.P, 4)));
-    const int S = pick_cluster_size(B, a.P, slots, 256);
+    const int S = pick_cluster_size(GSSD_KERNEL_MATCH, B, a.P);
     a.slice = ceil_div(a.P, S);
     size_t smem = match_smem_bytes(g_max, a.slice);
     cudaLaunchConfig_t cfg = {};
