@@ -89,6 +89,7 @@ class BackboneRun(object):
     def __init__(self, modules):
         self.modules = list(modules)
         self._packed = {}
+        self._too_wide = set()
 
     def _conv(self, i, conv, bn, dev):
         key = (_versions(conv, bn), str(dev))
@@ -116,10 +117,21 @@ class BackboneRun(object):
                 relu = j < stop and isinstance(mods[j], nn.ReLU)
                 if bn is not None and bn.training:
                     raise NotImplementedError("BackboneRun folds BatchNorm: eval mode only")
-                if not isinstance(x, PM):
-                    x = PM.from_nchw(x)
-                cv = self._conv(i, m, bn, x.data.device)
-                x = conv_igemm(x, cv, relu=relu, scale=cv.scale, shift=cv.shift)
+                if i in self._too_wide:                              # the slab of this feature-map width does not fit: torch
+                    if isinstance(x, PM):
+                        x = x.to_nchw()
+                    x = m(x)
+                    i += 1
+                    continue
+                xin = x if isinstance(x, PM) else PM.from_nchw(x)
+                cv = self._conv(i, m, bn, xin.data.device)
+                try:
+                    x = conv_igemm(xin, cv, relu=relu, scale=cv.scale, shift=cv.shift)
+                except RuntimeError as e:
+                    if "GSSD_MAX" not in str(e) and "limits" not in str(e):
+                        raise
+                    self._too_wide.add(i)
+                    continue
                 i = j + (1 if relu else 0)
             elif isinstance(m, nn.MaxPool2d) and isinstance(x, PM):
                 x = maxpool_pm(x, m)
