@@ -136,7 +136,8 @@ def test_match_empty_raises():
 
 
 @pytest.mark.parametrize("B,gmax,pname", [(1, 5, "v2"), (8, 5, "v2"), (40, 12, "v2"), (3, 32, "v2_512"),
-                                          (300, 3, "small"), (5, 100, "v2_custom_512")])
+                                          (300, 3, "small"), (5, 100, "v2_custom_512"),
+                                          (80, 3, "v2"), (90, 32, "v2_512")])            # beyond 74 images: 2 CTAs per image
 def test_match_batched_vs_oracle(B, gmax, pname):
     """every cluster configuration (8/4/2/1 CTAs per image) and ragged G"""
     pri = cases.priors(pname)
@@ -210,7 +211,9 @@ def test_multibox_loss_golden(tag):
 
 
 @pytest.mark.parametrize("B,gmax,pname,C", [(1, 5, "v2", 2), (32, 5, "v2", 2), (50, 8, "v2", 2), (160, 5, "v2", 2),
-                                            (310, 3, "small", 2), (6, 32, "v2_512", 2), (4, 6, "v2", 4)])
+                                            (310, 3, "small", 2), (6, 32, "v2_512", 2), (4, 6, "v2", 4),
+                                            (80, 32, "v2_512", 2),                       # configs[4] shape: 4 CTAs per image
+                                            (600, 2, "v2", 2)])                           # beyond batch 512: 1 CTA per image
 def test_multibox_loss_vs_oracle(B, gmax, pname, C):
     pri = cases.priors(pname)
     r = syn.rng(200 + B)
@@ -345,6 +348,8 @@ def test_detect_errors_and_devices():
     (2, "v2", 5, -1.0, 0.1, 0.05, 64),         # several classes, other top_k
     (2, "v2_custom_512", 2, 0.0, 0.05, 0.5, 1000),
     (3, "small", 2, 0.0, 0.3, 0.1, 200),       # n_cand < top_k
+    (256, "v2", 2, -4.0, 0.5, 0.2, 200),       # configs[3]: batch 256 inference sweep (no helper CTAs, 2 CTAs per SM)
+    (40, "v2", 2, -4.0, 0.5, 0.2, 200),        # 2 helper CTAs per image
 ])
 def test_detect_vs_oracle(B, pname, C, shift, sigma, thr, top_k):
     pri = cases.priors(pname)
