@@ -85,3 +85,16 @@ def test_shard_and_header_helpers():
     h = torch.cat([gdist.make_header(1.5, 7), gdist.make_header(-2.0, 5), gdist.make_header(0.25, 0)])
     assert gdist.combine_headers(h) == (1.5, 12)
     assert gdist.world()[1:] == (1, 0)
+
+
+def test_peer_exchange_is_off_without_cuda_or_nccl():
+    """host logic: the NVLink peer exchange is only offered for NCCL groups on CUDA devices; everything else keeps the
+    all-gather of the 16-byte headers"""
+    from grouped_ssd_pytorch_b200 import dist as gdist
+    assert gdist.peer_exchange(None) is None          # no process group in this process
+    import os
+    os.environ["GSSD_PEER_XCHG"] = "0"
+    try:
+        assert gdist.peer_exchange(None) is None
+    finally:
+        del os.environ["GSSD_PEER_XCHG"]
