@@ -35,9 +35,3 @@ torch.backends.cudnn.allow_tf32 = False
 for bb in (False, True):
     ms = timeit(lambda: gssd_forward(net, x, backbone=bb))
     print("gssd_forward backbone=%-5s             : %7.3f ms  %8.0f img/s" % (bb, ms, B / ms * 1e3), flush=True)
-nb = net.to(torch.bfloat16).to(memory_format=torch.channels_last); xb = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-try:
-    net.L2Norm.float()
-    ms = timeit(lambda: [nb.vgg[k] for k in range(0)] or None)
-except Exception:
-    pass
