@@ -150,3 +150,28 @@ def test_full_size_source1_linearity_and_oracle_sample():
             patch = xp[n, g * (C // groups):(g + 1) * (C // groups), yy:yy + 3, xx:xx + 3].astype(np.float64)
             want = float((patch * w[co].astype(np.float64)).sum())
             assert abs(y1[n, co, yy, xx] - want) <= 2e-2 + 4e-3 * abs(want), (n, yy, xx, co, y1[n, co, yy, xx], want)
+
+
+def test_train_mode_channel_statistics_at_full_size():
+    """the per-channel sum / sum of squares the conv epilogue accumulates for train-mode BatchNorm (warp-transposed partial
+    sums + red.add from ~400 tiles) against torch's own statistics of the same convolution, source-1 size, batch 4"""
+    from grouped_ssd_pytorch_b200.layers.modules.source_block import PM, _Conv, conv_igemm
+    r = np.random.RandomState(11)
+    N, C, H, W, groups = 4, 512, 38, 38, 4
+    x = torch.from_numpy(SB.bf16_round(np.maximum(r.randn(N, C, H, W), 0).astype(np.float32))).cuda()
+    conv = nn.Conv2d(C, C, 3, padding=1, groups=groups).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(torch.from_numpy(SB.bf16_round((r.randn(C, C // groups, 3, 3) * 0.03).astype(np.float32))))
+        conv.bias.copy_(torch.from_numpy((r.randn(C) * 0.1).astype(np.float32)))
+        torch.backends.cudnn.allow_tf32 = False
+        ref = conv(x)
+    cv = _Conv(conv, groups, dev=x.device)
+    stats = torch.zeros(2 * C, device="cuda")
+    y = conv_igemm(PM.from_nchw(x), cv, relu=False, shift=cv.bias, chan_sum=stats)
+    n = N * H * W
+    mean = stats[:C] / n
+    var = stats[C:] / n - mean * mean
+    np.testing.assert_allclose(mean.cpu().numpy(), ref.mean(dim=(0, 2, 3)).cpu().numpy(), rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(var.cpu().numpy(), ref.var(dim=(0, 2, 3), unbiased=False).cpu().numpy(), rtol=2e-3, atol=1e-5)
+    # against cuDNN's accumulation order a value may round to the neighbouring bf16: one ulp of the top binade = 2^-7 of the max
+    assert rel(y.to_nchw().cpu().numpy(), SB.bf16_round(ref.cpu().numpy())) <= 2.0 ** -7
