@@ -3,8 +3,9 @@
 The only exchange on the hot path is the pair of batch-global scalars of MultiBoxLoss — the max of conf
 (box_utils.py:167) and the number of positives N (multibox_loss.py:117) — which the reference computes on
 the batch gathered by DataParallel on GPU 0 (train_lesion_multiphase_v2.py:242-246).  Each rank's stage-1
-kernel leaves them in a 16-byte header (`gssd_loss_stats`, include/gssd.h); the headers are all-gathered
-(NCCL over NVLink on GPUs, gloo in the CPU tests) and stage 2 reduces them in-kernel (MAX / SUM).
+kernel leaves them in a 16-byte header (`gssd_loss_stats`, include/gssd.h).  On one NVLink box the header travels as
+peer stores from that kernel's last CTA into every rank's exchange buffer (`PeerExchange`); otherwise the headers are
+all-gathered (NCCL, or gloo in the CPU tests).  Stage 2 reduces them in-kernel (MAX / SUM) either way.
 Detect needs no exchange: its outputs are per image.
 """
 import numpy as np
