@@ -53,7 +53,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gconv", action="store_true", help="skip the tensor-core source-block measurement")
-    ap.add_argument("--sweep", action="store_true", help="also report the kernels' roofline at larger batches")
+    ap.add_argument("--sweep", action="store_true", help="(default at N=1) also report the kernels' roofline at larger batches")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the large-batch roofline sweep")
     return ap.parse_args()
 
 
@@ -440,7 +441,7 @@ def run_ours(a):
                 line["gconv"] = time_gconv(a, torch, dev, B)
             except Exception as e:                               # pragma: no cover
                 line["gconv"] = {"error": repr(e)}
-        if a.sweep:
+        if (a.sweep or world == 1) and not a.no_sweep:
             line["roofline_sweep"] = sweep(a, lib, _lib, torch, dev, pack_targets)
         print(json.dumps(line), flush=True)
     if world > 1:
