@@ -216,16 +216,20 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
     GSSD_PHASE(match, 1, dbg);
 
     // ---- best prior per GT over the whole image, then the sequential force match -------------------
-    if (nranks > 1) cluster.sync();
-    for (int g = tid; g < G; g += MATCH_NT) {
-        unsigned long long m = sbest[g];
-        for (unsigned r = 0; r < nranks; ++r) {
-            if (r == rank) continue;
-            const unsigned long long o = cluster.map_shared_rank(sbest, r)[g];
-            m = o > m ? o : m;
+    if (nranks > 1) {
+        cluster.sync();
+        // one thread per (GT row, peer CTA): the remote reads of the per-slice maxima go out together instead of one
+        // distributed-shared-memory round trip after the other
+        for (unsigned i = tid; i < (unsigned)G * nranks; i += MATCH_NT) {
+            const unsigned g = i / nranks, r = i - g * nranks;
+            if (r != rank) {
+                const unsigned long long o = cluster.map_shared_rank(sbest, r)[g];
+                if (o > sbest[g]) atomicMax(&sbest[g], o);
+            }
         }
-        sbp[g] = (int)(0xffffffffu - (unsigned)(m & 0xffffffffu));
+        __syncthreads();
     }
+    for (int g = tid; g < G; g += MATCH_NT) sbp[g] = (int)(0xffffffffu - (unsigned)(sbest[g] & 0xffffffffu));
     __syncthreads();
     if (tid == 0) {
         for (int g = 0; g < G; ++g) {                            // box_utils.py:101-105, in GT order

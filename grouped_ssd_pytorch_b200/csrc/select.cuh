@@ -76,8 +76,15 @@ __device__ unsigned long long radix_select(const uint32_t *keys, int n_local, ui
         if (CLUSTER) {
             cluster.sync();
             for (int i = tid; i < 256; i += NT) {
+                // the (up to 8) remote reads are independent: unrolled so that they are in flight together instead of one
+                // distributed-shared-memory round trip after the other
+                uint32_t part[8];
+#pragma unroll
+                for (unsigned r = 0; r < 8; ++r) part[r] = r < nranks ? cluster.map_shared_rank(&s->hist[buf][0], r)[i] : 0u;
                 uint32_t t = 0;
-                for (unsigned r = 0; r < nranks; ++r) t += cluster.map_shared_rank(&s->hist[buf][0], r)[i];
+#pragma unroll
+                for (unsigned r = 0; r < 8; ++r) t += part[r];
+                for (unsigned r = 8; r < nranks; ++r) t += cluster.map_shared_rank(&s->hist[buf][0], r)[i];
                 s->total[i] = t;
             }
             tot = s->total;
