@@ -69,8 +69,14 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
     __shared__ int s_nlist;
     __shared__ bool s_is_last;
 
+    // conf-max pass: a contiguous slice per CTA (uniform, streaming work)
     const int p0 = rank * a.slice;
     const int p1 = min(a.P, p0 + a.slice);
+    // IoU sweep: the CTAs of the image own the priors in interleaved chunks of MATCH_NT (CTA r: chunks r, r + S, ...).  The
+    // work per prior depends on how many GT boxes it overlaps — the large priors at the end of the list overlap most of
+    // them — so contiguous slices leave the first CTAs waiting for the last ones at the cluster barrier.
+    const int n_chunks = (a.P + MATCH_NT - 1) / MATCH_NT;
+    const int my_chunks = (int)rank < n_chunks ? (n_chunks - (int)rank + (int)nranks - 1) / (int)nranks : 0;
 
     for (int g = tid; g < G; g += MATCH_NT) {
         const float *row = a.gt + 5 * (size_t)(g0 + g);
@@ -88,7 +94,9 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
     // ---- optional: drop the GT boxes that cannot touch this CTA's slice of priors --------------------------
     if (G >= MATCH_CULL_MIN_G) {
         float bx1 = INFINITY, by1 = INFINITY, bx2 = -INFINITY, by2 = -INFINITY;
-        for (int p = p0 + tid; p < p1; p += MATCH_NT) {
+        for (int j = 0; j < my_chunks; ++j) {
+            const int p = ((int)rank + j * (int)nranks) * MATCH_NT + tid;
+            if (p >= a.P) continue;
             const float4 pb = point_form(a.priors[p]);
             bx1 = fminf(bx1, pb.x); by1 = fminf(by1, pb.y); bx2 = fmaxf(bx2, pb.z); by2 = fmaxf(by2, pb.w);
         }
@@ -155,13 +163,14 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
     // box, one GT per lane, and only the GT rows that hit it are swept.
     const bool warp_cull = n_list >= MATCH_CULL_MIN_G;
     const float4 far = make_float4(3e30f, 3e30f, 0.f, 0.f);
-    int pbase = p0 + warp * 32;
-    float4 nxt = (pbase + lane < p1) ? a.priors[pbase + lane] : far;
-    for (; pbase < p1; pbase += MATCH_NT) {
-        const int p = pbase + lane;
-        const bool valid = p < p1;
+    const int chunk_stride = (int)nranks * MATCH_NT;
+    float4 nxt = far;
+    if (my_chunks > 0) { const int pf = (int)rank * MATCH_NT + warp * 32 + lane; if (pf < a.P) nxt = a.priors[pf]; }
+    for (int j = 0; j < my_chunks; ++j) {
+        const int p = (int)rank * MATCH_NT + j * chunk_stride + warp * 32 + lane;
+        const bool valid = p < a.P;
         const float4 pb = point_form(nxt);
-        if (pbase + MATCH_NT < p1) nxt = (p + MATCH_NT < p1) ? a.priors[p + MATCH_NT] : far;   // prefetch
+        nxt = (j + 1 < my_chunks && p + chunk_stride < a.P) ? a.priors[p + chunk_stride] : far;   // prefetch
         const float area_b = box_area(pb);
         float best = 0.f;                                        // IoU >= 0: row 0 wins an all-zero column
         int bidx = 0;
@@ -210,7 +219,7 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
                 }
             }
         }
-        if (valid) stag[p - p0] = (uint16_t)(bidx | (!(best < a.threshold) ? 0x8000 : 0));   // box_utils.py:108
+        if (valid) stag[j * MATCH_NT + warp * 32 + lane] = (uint16_t)(bidx | (!(best < a.threshold) ? 0x8000 : 0));   // box_utils.py:108
     }
     __syncthreads();
     GSSD_PHASE(match, 1, dbg);
@@ -234,7 +243,8 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
     if (tid == 0) {
         for (int g = 0; g < G; ++g) {                            // box_utils.py:101-105, in GT order
             const int bp = sbp[g];
-            if (bp >= p0 && bp < p1) stag[bp - p0] = (uint16_t)(0x8000 | g);
+            const int ck = bp / MATCH_NT;
+            if (ck % (int)nranks == (int)rank) stag[(ck / (int)nranks) * MATCH_NT + bp % MATCH_NT] = (uint16_t)(0x8000 | g);
         }
     }
     __syncthreads();
@@ -242,8 +252,10 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
     GSSD_PHASE(match, 2, dbg);
     // ---- emit --------------------------------------------------------------------------------------
     int npos = 0;
-    for (int p = p0 + tid; p < p1; p += MATCH_NT) {
-        const uint16_t tag = stag[p - p0];
+    for (int j = 0; j < my_chunks; ++j) {
+        const int p = (int)rank * MATCH_NT + j * chunk_stride + tid;
+        if (p >= a.P) continue;
+        const uint16_t tag = stag[j * MATCH_NT + tid];
         const bool pos = tag & 0x8000;
         const int g = tag & 0x7fff;
         npos += pos;
@@ -309,7 +321,7 @@ static int launch_match(const MatchArgs &a_in, int B, int g_max, cudaStream_t st
     GSSD_RETURN_IF_CUDA(allow_max_smem(reinterpret_cast<const void *>(kern)));
     const int S = pick_cluster_size(GSSD_KERNEL_MATCH, B, a.P);
     a.slice = ceil_div(a.P, S);
-    size_t smem = match_smem_bytes(g_max, a.slice);
+    size_t smem = match_smem_bytes(g_max, ceil_div(ceil_div(a.P, MATCH_NT), S) * MATCH_NT);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(S, B, 1);
     cfg.blockDim = dim3(MATCH_NT, 1, 1);
