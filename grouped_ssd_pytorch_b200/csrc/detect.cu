@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(DET_NT, CL ? 1 : 2) detect_kernel(DetArgs a) {
                 if (cand && slot < DET_CAND_CAP) ckey[slot] = ((unsigned long long)key << 32) | (unsigned)p;
             }
         };
-        constexpr int U = CL ? 2 : 4;            // loads in flight per thread (a cluster CTA owns about one float4 per thread)
+        constexpr int U = CL ? 3 : 4;            // loads in flight per thread: with 2 CTAs per image a CTA owns 2.1 float4 per thread at
+                                                 // P = 8732 -> one round of loads
         if (!NMS_MODE && a.C == 2 && (n & 1) == 0) {
             // rows are (background, class 1) pairs: one float4 = two priors, the .y / .w lanes are ours
             const float4 *src = reinterpret_cast<const float4 *>(a.conf + (size_t)b * a.P * 2);
