@@ -46,7 +46,7 @@ static size_t match_smem_bytes(int g_max, int slice) {
 constexpr int MATCH_CULL_MIN_G = 8;       // below this the bounding-box pre-pass costs more than it saves
 
 template <bool MATERIALISE, bool CONF_MAX>
-__global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
+__global__ void __launch_bounds__(MATCH_NT, 6) match_kernel(MatchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned nranks = cluster.num_blocks();
@@ -134,27 +134,13 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
     const bool dbg = blockIdx.x == 0 && blockIdx.y == 0;
     GSSD_PHASE(match, 0, dbg);
 
-    // ---- batch max of conf over this CTA's rows: a streaming, vectorised pass of its own ----------------
+    // ---- batch max of conf, part 1: ask L2 for this CTA's rows now; they are reduced after the IoU sweep, which needs no
+    // HBM traffic of its own (the priors stay in L2), so the DRAM latency / transfer hides behind it ----------------
     if (CONF_MAX && p1 > p0) {
-        const float *src = a.conf + ((size_t)b * a.P + p0) * a.C;
-        const size_t n = (size_t)(p1 - p0) * a.C;
-        size_t head = ((16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15) >> 2;   // floats up to 16-byte alignment
-        if (head > n) head = n;
-        const size_t n4 = (n - head) >> 2;
-        const float4 *src4 = reinterpret_cast<const float4 *>(src + head);
-        for (size_t i = tid; i < head; i += MATCH_NT) cmax = fmaxf(cmax, src[i]);
-        constexpr int U = 4;
-        for (size_t base = 0; base < n4; base += MATCH_NT * U) {
-            float4 v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const size_t i = base + (size_t)u * MATCH_NT + tid;
-                v[u] = i < n4 ? ldg_stream(src4 + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) cmax = fmaxf(cmax, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
-        }
-        for (size_t i = head + 4 * n4 + tid; i < n; i += MATCH_NT) cmax = fmaxf(cmax, src[i]);
+        const char *c0 = reinterpret_cast<const char *>(a.conf + ((size_t)b * a.P + p0) * a.C);
+        const size_t nbytes = (size_t)(p1 - p0) * a.C * sizeof(float);
+        for (size_t o = (size_t)tid * 128; o < nbytes; o += (size_t)MATCH_NT * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(c0 + o));
     }
 
     // ---- IoU sweep, one warp per 32 consecutive priors ------------------------------------------------------
@@ -178,23 +164,27 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
             const float4 t = sgt4[g];
             const float iw = __fsub_rn(fminf(t.z, pb.z), fmaxf(t.x, pb.x));
             const float ih = __fsub_rn(fminf(t.w, pb.w), fmaxf(t.y, pb.y));
-            if (valid && iw > 0.f && ih > 0.f) {                 // rare: the boxes overlap
+            if (iw > 0.f && ih > 0.f) {                          // the boxes overlap (never for the 'far' prior of an invalid lane)
                 const float inter = __fmul_rn(iw, ih);
                 const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(sarea[g], area_b), inter));
                 if (iou > best) { best = iou; bidx = g; }        // first max over GT (torch.max dim 0)
-                // best prior of this GT: max of (IoU bits, ~prior) over whichever lanes are here together;
-                // IoU >= +0 so the uint order of the bits is the float order, ~prior breaks ties downwards
-                const unsigned act = __activemask();
+                // best prior of this GT: max of (IoU bits, ~prior); IoU >= +0 so the uint order of the bits is the float
+                // order, ~prior breaks ties downwards.  Only the lanes that beat the running maximum (few, after the first
+                // rows) go on to the warp reduction and the shared-memory atomic.
                 const unsigned bits = __float_as_uint(iou);
-                const unsigned m = __reduce_max_sync(act, bits);
-                const unsigned who = __ballot_sync(act, bits == m);
-                if (lane == __ffs(who) - 1) {
-                    const unsigned long long key = ((unsigned long long)m << 32) | (0xffffffffu - (unsigned)p);
-                    if (key > sbest[g]) atomicMax(&sbest[g], key);
+                const unsigned long long key = ((unsigned long long)bits << 32) | (0xffffffffu - (unsigned)p);
+                if (key > sbest[g]) {
+                    const unsigned act = __activemask();
+                    const unsigned m = __reduce_max_sync(act, bits);
+                    const unsigned who = __ballot_sync(act, bits == m);
+                    if (lane == __ffs(who) - 1) atomicMax(&sbest[g], key);
                 }
             }
         };
-        if (!warp_cull) {
+        if (G < MATCH_CULL_MIN_G) {                              // no culling at all: glist is the identity
+#pragma unroll 1
+            for (int g = 0; g < G; ++g) sweep_one(g);
+        } else if (!warp_cull) {
             for (int q = 0; q < n_list; ++q) sweep_one(glist[q]);
         } else {
             float bx1 = valid ? pb.x : INFINITY, by1 = valid ? pb.y : INFINITY;
@@ -220,6 +210,28 @@ __global__ void __launch_bounds__(MATCH_NT) match_kernel(MatchArgs a) {
             }
         }
         if (valid) stag[j * MATCH_NT + warp * 32 + lane] = (uint16_t)(bidx | (!(best < a.threshold) ? 0x8000 : 0));   // box_utils.py:108
+    }
+    // ---- batch max of conf, part 2: a streaming, vectorised pass over the rows prefetched above ---------
+    if (CONF_MAX && p1 > p0) {
+        const float *src = a.conf + ((size_t)b * a.P + p0) * a.C;
+        const size_t n = (size_t)(p1 - p0) * a.C;
+        size_t head = ((16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15) >> 2;   // floats up to 16-byte alignment
+        if (head > n) head = n;
+        const size_t n4 = (n - head) >> 2;
+        const float4 *src4 = reinterpret_cast<const float4 *>(src + head);
+        for (size_t i = tid; i < head; i += MATCH_NT) cmax = fmaxf(cmax, src[i]);
+        constexpr int U = 4;
+        for (size_t base = 0; base < n4; base += MATCH_NT * U) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const size_t i = base + (size_t)u * MATCH_NT + tid;
+                v[u] = i < n4 ? ldg_stream(src4 + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) cmax = fmaxf(cmax, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
+        }
+        for (size_t i = head + 4 * n4 + tid; i < n; i += MATCH_NT) cmax = fmaxf(cmax, src[i]);
     }
     __syncthreads();
     GSSD_PHASE(match, 1, dbg);
