@@ -18,6 +18,9 @@ GSSD_PHASE_DECL(match)
 namespace gssd {
 
 constexpr int MATCH_NT = 256;
+#ifndef GSSD_MATCH_MIN_CTAS
+#define GSSD_MATCH_MIN_CTAS 5                  // resident CTAs per SM the register allocation is held to
+#endif
 
 struct MatchArgs {
     const float4 *priors; int P;
@@ -29,6 +32,7 @@ struct MatchArgs {
     int32_t *num_pos;                         // [B] or null
     float4 *loc_t; int64_t *conf_t; int32_t *bti_out;   // materialised outputs or null
     int slice;                                // priors per CTA
+    int S;                                    // CTAs per image (cluster size)
     XDev x;                                   // peer exchange of the statistics (world == 0: off)
 };
 
@@ -46,7 +50,7 @@ static size_t match_smem_bytes(int g_max, int slice) {
 constexpr int MATCH_CULL_MIN_G = 8;       // below this the bounding-box pre-pass costs more than it saves
 
 template <bool MATERIALISE, bool CONF_MAX>
-__global__ void __launch_bounds__(MATCH_NT, 6) match_kernel(MatchArgs a) {
+__global__ void __launch_bounds__(MATCH_NT, GSSD_MATCH_MIN_CTAS) match_kernel(MatchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned nranks = cluster.num_blocks();
@@ -148,15 +152,17 @@ __global__ void __launch_bounds__(MATCH_NT, 6) match_kernel(MatchArgs a) {
     // priors of a warp (neighbouring cells / anchors) first test the GT list against their common bounding
     // box, one GT per lane, and only the GT rows that hit it are swept.
     const bool warp_cull = n_list >= MATCH_CULL_MIN_G;
-    const float4 far = make_float4(3e30f, 3e30f, 0.f, 0.f);
-    const int chunk_stride = (int)nranks * MATCH_NT;
-    float4 nxt = far;
-    if (my_chunks > 0) { const int pf = (int)rank * MATCH_NT + warp * 32 + lane; if (pf < a.P) nxt = a.priors[pf]; }
-    for (int j = 0; j < my_chunks; ++j) {
-        const int p = (int)rank * MATCH_NT + j * chunk_stride + warp * 32 + lane;
-        const bool valid = p < a.P;
+    const int chunk_stride = a.S * MATCH_NT;                     // a.S == nranks, as a kernel constant
+    // a lane past the end of the list repeats the LAST prior: it produces that prior's own (IoU, index) keys a second time,
+    // which the running maxima ignore, and its tag lands in the padding of the chunk
+    const int p_last = a.P - 1;
+    int p = (int)rank * MATCH_NT + tid;
+    uint16_t *stag_w = stag + tid;
+    float4 nxt = a.priors[min(p, p_last)];
+    for (int j = my_chunks; j > 0; --j, p += chunk_stride, stag_w += MATCH_NT) {
+        const int pc = min(p, p_last);
         const float4 pb = point_form(nxt);
-        nxt = (j + 1 < my_chunks && p + chunk_stride < a.P) ? a.priors[p + chunk_stride] : far;   // prefetch
+        nxt = a.priors[min(p + chunk_stride, p_last)];           // prefetch (the last round re-reads a cached row)
         const float area_b = box_area(pb);
         float best = 0.f;                                        // IoU >= 0: row 0 wins an all-zero column
         int bidx = 0;
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(MATCH_NT, 6) match_kernel(MatchArgs a) {
             const float4 t = sgt4[g];
             const float iw = __fsub_rn(fminf(t.z, pb.z), fmaxf(t.x, pb.x));
             const float ih = __fsub_rn(fminf(t.w, pb.w), fmaxf(t.y, pb.y));
-            if (iw > 0.f && ih > 0.f) {                          // the boxes overlap (never for the 'far' prior of an invalid lane)
+            if (iw > 0.f && ih > 0.f) {                          // the boxes overlap
                 const float inter = __fmul_rn(iw, ih);
                 const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(sarea[g], area_b), inter));
                 if (iou > best) { best = iou; bidx = g; }        // first max over GT (torch.max dim 0)
@@ -172,7 +178,7 @@ __global__ void __launch_bounds__(MATCH_NT, 6) match_kernel(MatchArgs a) {
                 // order, ~prior breaks ties downwards.  Only the lanes that beat the running maximum (few, after the first
                 // rows) go on to the warp reduction and the shared-memory atomic.
                 const unsigned bits = __float_as_uint(iou);
-                const unsigned long long key = ((unsigned long long)bits << 32) | (0xffffffffu - (unsigned)p);
+                const unsigned long long key = ((unsigned long long)bits << 32) | (0xffffffffu - (unsigned)pc);
                 if (key > sbest[g]) {
                     const unsigned act = __activemask();
                     const unsigned m = __reduce_max_sync(act, bits);
@@ -187,8 +193,7 @@ __global__ void __launch_bounds__(MATCH_NT, 6) match_kernel(MatchArgs a) {
         } else if (!warp_cull) {
             for (int q = 0; q < n_list; ++q) sweep_one(glist[q]);
         } else {
-            float bx1 = valid ? pb.x : INFINITY, by1 = valid ? pb.y : INFINITY;
-            float bx2 = valid ? pb.z : -INFINITY, by2 = valid ? pb.w : -INFINITY;
+            float bx1 = pb.x, by1 = pb.y, bx2 = pb.z, by2 = pb.w;
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
                 bx1 = fminf(bx1, __shfl_xor_sync(FULL, bx1, o)); by1 = fminf(by1, __shfl_xor_sync(FULL, by1, o));
@@ -209,7 +214,7 @@ __global__ void __launch_bounds__(MATCH_NT, 6) match_kernel(MatchArgs a) {
                 }
             }
         }
-        if (valid) stag[j * MATCH_NT + warp * 32 + lane] = (uint16_t)(bidx | (!(best < a.threshold) ? 0x8000 : 0));   // box_utils.py:108
+        *stag_w = (uint16_t)(bidx | (!(best < a.threshold) ? 0x8000 : 0));   // box_utils.py:108
     }
     // ---- batch max of conf, part 2: a streaming, vectorised pass over the rows prefetched above ---------
     if (CONF_MAX && p1 > p0) {
@@ -333,6 +338,7 @@ static int launch_match(const MatchArgs &a_in, int B, int g_max, cudaStream_t st
     GSSD_RETURN_IF_CUDA(allow_max_smem(reinterpret_cast<const void *>(kern)));
     const int S = pick_cluster_size(GSSD_KERNEL_MATCH, B, a.P);
     a.slice = ceil_div(a.P, S);
+    a.S = S;
     size_t smem = match_smem_bytes(g_max, ceil_div(ceil_div(a.P, MATCH_NT), S) * MATCH_NT);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(S, B, 1);

@@ -3,6 +3,9 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
+from grouped_ssd_pytorch_b200 import build as _b
+if os.environ.get("GSSD_ALT_LIB"):          # development: time an alternative build of the library
+    _b.LIB = os.path.abspath(os.environ["GSSD_ALT_LIB"]); _b.stale = lambda: False
 from grouped_ssd_pytorch_b200 import _lib, config, synthetic as syn
 from grouped_ssd_pytorch_b200.layers import PriorBox
 from grouped_ssd_pytorch_b200.layers.box_utils import pack_target_list
