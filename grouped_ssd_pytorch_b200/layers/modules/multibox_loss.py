@@ -63,6 +63,7 @@ class _MultiBoxLossFn(torch.autograd.Function):
                                           losses.data_ptr(), _lib.ptr(grad_loc), _lib.ptr(grad_conf),
                                           _lib.ptr(pos), _lib.ptr(neg), ws.data_ptr(), ws_bytes, st), "gssd_mbox_loss")
         ctx.grads = (grad_loc, grad_conf)
+        ctx.set_materialize_grads(False)       # no zero tensors for the outputs nobody differentiates (num_pos, an unused loss)
         num_pos = stats[_lib.STATS_HEADER_BYTES:].view(torch.int32)
         aux = [t for t in (pos, neg, num_pos) if t is not None]
         ctx.mark_non_differentiable(*aux)
@@ -76,6 +77,10 @@ class _MultiBoxLossFn(torch.autograd.Function):
             return (None,) * 12
         lib = _lib.load()
         with torch.cuda.device(grad_loc.device):
+            if g_l is None:                    # that loss took no part in what was differentiated
+                g_l = torch.zeros((), dtype=torch.float32, device=grad_loc.device)
+            if g_c is None:
+                g_c = torch.zeros((), dtype=torch.float32, device=grad_loc.device)
             if not (g_l.is_cuda and g_l.dtype == torch.float32):
                 g_l = g_l.to(device=grad_loc.device, dtype=torch.float32)
             if not (g_c.is_cuda and g_c.dtype == torch.float32):

@@ -260,6 +260,12 @@ def test_multibox_loss_api_variants():
     (2.0 * ll + 0.5 * lc).backward()
     close(l.grad, 2.0 * base[2].cpu().numpy(), rtol=1e-6, atol=1e-12)
     close(c.grad, 0.5 * base[3].cpu().numpy(), rtol=1e-6, atol=1e-12)
+    # only one of the two losses differentiated: the other one's upstream gradient is absent, not a zero tensor
+    l = cu(loc).requires_grad_(); c = cu(conf).requires_grad_()
+    ll, lc = crit((l, c, cu(pri)), [cu(t) for t in tg])
+    ll.backward()
+    eq(l.grad, base[2].cpu().numpy())
+    assert c.grad is None or not c.grad.any()
     with pytest.raises(IndexError):
         crit((cu(loc), cu(conf), cu(pri)), [cu(tg[0]), torch.zeros(0, 5).cuda(), cu(tg[2]), cu(tg[3])])
 
