@@ -1,6 +1,7 @@
 // pipe.cu — host-buffer pipeline over the multibox kernels (include/gssd.h: gssd_pipe_*): the hot path as one native
 // call per step with HOST inputs and outputs, `depth` steps in flight on three streams (H2D copies | match + loss |
 // Detect), so that PCIe traffic, kernels and the device->host results of neighbouring steps overlap.
+#include <initializer_list>
 #include <new>
 
 #include "common.cuh"
@@ -58,8 +59,16 @@ int64_t begin_step(gssd_pipe *p, const float *loc_h, const float *conf_h, const 
     const gssd_pipe_cfg &c = p->cfg;
     if (!loc_h || !conf_h || !gt_h || !gt_off_h || sum_g <= 0 || g_max <= 0) return GSSD_ERR_ARG;
     if (sum_g > c.max_gt_rows) return GSSD_ERR_LIMIT;
+    // the row offsets are host memory: check them here, the kernels size their shared memory from g_max and index gt by them
+    if (gt_off_h[0] != 0 || gt_off_h[c.B] != sum_g) return GSSD_ERR_ARG;
+    for (int b = 0; b < c.B; ++b) {
+        const int rows = gt_off_h[b + 1] - gt_off_h[b];
+        if (rows <= 0) return rows == 0 ? GSSD_ERR_EMPTY : GSSD_ERR_ARG;
+        if (rows > g_max) return GSSD_ERR_ARG;
+    }
     const int64_t ticket = p->next;
     const int k = (int)(ticket % c.depth);
+    if (p->begun[k]) return GSSD_ERR_ARG;                                    // gssd_pipe_begin `depth` steps ago was never finished
     if (p->busy[k]) { PIPE_CUDA(cudaEventSynchronize(p->ev_done[k])); p->busy[k] = false; }
     const gssd_pipe_slot &s = p->slot[k];
     const size_t BP = (size_t)c.B * c.P, n_loc = BP * 4 * 4, n_conf = BP * c.C * 4;
@@ -130,6 +139,8 @@ extern "C" size_t gssd_pipe_arena_bytes(const gssd_pipe_cfg *cfg) {
     return layout_slot(*cfg, nullptr, nullptr) * (size_t)cfg->depth + 256;
 }
 
+extern "C" void gssd_pipe_destroy(gssd_pipe *p);
+
 extern "C" int gssd_pipe_create(gssd_pipe **out, const gssd_pipe_cfg *cfg, const float *priors, void *arena, size_t arena_bytes) {
     if (!out || !cfg_ok(cfg) || !priors || !arena) return GSSD_ERR_ARG;
     if (cfg->P > GSSD_MAX_PRIORS || cfg->top_k > GSSD_MAX_TOP_K || cfg->C > GSSD_MAX_CLASSES) return GSSD_ERR_LIMIT;
@@ -138,6 +149,8 @@ extern "C" int gssd_pipe_create(gssd_pipe **out, const gssd_pipe_cfg *cfg, const
     gssd_pipe *p = new (std::nothrow) gssd_pipe();
     if (!p) return GSSD_ERR_ARG;
     p->cfg = *cfg; p->priors = priors; p->next = 0; p->use_x = false; p->det_logits = false;
+    p->s_copy = p->s_main = p->s_side = nullptr;
+    for (int k = 0; k < 8; ++k) p->ev_in[k] = p->ev_free[k] = p->ev_side[k] = p->ev_done[k] = nullptr;
     for (int i = 0; i < GSSD_MAX_CLASSES; ++i) p->class_bias[i] = 0.f;
     uint8_t *base = (uint8_t *)(((uintptr_t)arena + 255) & ~(uintptr_t)255);
     const size_t per = layout_slot(*cfg, nullptr, nullptr);
@@ -155,18 +168,18 @@ extern "C" int gssd_pipe_create(gssd_pipe **out, const gssd_pipe_cfg *cfg, const
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_side[k], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_done[k], cudaEventDisableTiming);
     }
-    if (e != cudaSuccess) { delete p; return (int)e; }
+    if (e != cudaSuccess) { gssd_pipe_destroy(p); return (int)e; }
     *out = p;
     return GSSD_OK;
 }
 
 extern "C" void gssd_pipe_destroy(gssd_pipe *p) {
     if (!p) return;
-    cudaStreamSynchronize(p->s_copy); cudaStreamSynchronize(p->s_main); cudaStreamSynchronize(p->s_side);
-    for (int k = 0; k < p->cfg.depth; ++k) {
-        cudaEventDestroy(p->ev_in[k]); cudaEventDestroy(p->ev_free[k]); cudaEventDestroy(p->ev_side[k]); cudaEventDestroy(p->ev_done[k]);
-    }
-    cudaStreamDestroy(p->s_copy); cudaStreamDestroy(p->s_main); cudaStreamDestroy(p->s_side);
+    // also the unwinding path of a gssd_pipe_create that failed half-way: handles that were never created are null
+    for (cudaStream_t st : {p->s_copy, p->s_main, p->s_side}) if (st) cudaStreamSynchronize(st);
+    for (int k = 0; k < 8; ++k)
+        for (cudaEvent_t ev : {p->ev_in[k], p->ev_free[k], p->ev_side[k], p->ev_done[k]}) if (ev) cudaEventDestroy(ev);
+    for (cudaStream_t st : {p->s_copy, p->s_main, p->s_side}) if (st) cudaStreamDestroy(st);
     delete p;
 }
 

@@ -47,35 +47,47 @@ class PeerExchange(object):
     last CTA stores into all peers, stage 2 spins on the local copy — no collective call, graph-capturable."""
 
     def __init__(self, group=None):
+        """Collective over `group`.  Never raises between its collectives: a rank that fails (no IPC, ranks on several
+        hosts, no peer access) records `self.error` and still takes part in every exchange, so that the others do not hang;
+        `peer_exchange()` then agrees on the outcome with one all-reduce."""
         import ctypes as C
         from . import _lib
         lib = _lib.require_cuda()
         dist, ws, rank = world(group)
-        if ws > _lib.XCHG_MAX_RANKS:
-            raise RuntimeError("peer exchange supports up to %d ranks" % _lib.XCHG_MAX_RANKS)
-        self.lib, self.opened = lib, []
-        own = C.c_void_p()
+        self.lib, self.opened, self.own, self.x, self.error = lib, [], None, None, None
         handle = (C.c_ubyte * _lib.XCHG_HANDLE_BYTES)()
-        _lib.check(lib.gssd_xchg_create(C.byref(own), handle), "gssd_xchg_create")
-        self.own = own
-        mine = (bytes(handle), torch.cuda.current_device(), _hostname())
+        try:
+            if ws > _lib.XCHG_MAX_RANKS:
+                raise RuntimeError("peer exchange supports up to %d ranks" % _lib.XCHG_MAX_RANKS)
+            own = C.c_void_p()
+            _lib.check(lib.gssd_xchg_create(C.byref(own), handle), "gssd_xchg_create")
+            self.own = own
+        except Exception as e:
+            self.error = e
+        mine = (bytes(handle) if self.error is None else None, torch.cuda.current_device(), _hostname())
         everyone = [None] * ws
         dist.all_gather_object(everyone, mine, group=group)
-        if any(h[2] != mine[2] for h in everyone):
-            raise RuntimeError("peer exchange needs all ranks on one host")
-        x = _lib.Xchg()
-        x.rank, x.world = rank, ws
-        for r, (hb, _, _) in enumerate(everyone):
-            if r == rank:
-                x.peers[r] = own.value
-            else:
-                ptr = C.c_void_p()
-                buf = (C.c_ubyte * _lib.XCHG_HANDLE_BYTES).from_buffer_copy(hb)
-                _lib.check(lib.gssd_xchg_open(buf, C.byref(ptr)), "gssd_xchg_open")
-                self.opened.append(ptr)
-                x.peers[r] = ptr.value
-        self.x = x
-        dist.barrier(group=group)                                # every rank has mapped every buffer before first use
+        if self.error is not None:
+            return
+        try:
+            if any(h[0] is None for h in everyone):
+                raise RuntimeError("a rank could not create its exchange buffer")
+            if any(h[2] != mine[2] for h in everyone):
+                raise RuntimeError("peer exchange needs all ranks on one host")
+            x = _lib.Xchg()
+            x.rank, x.world = rank, ws
+            for r, (hb, _, _) in enumerate(everyone):
+                if r == rank:
+                    x.peers[r] = self.own.value
+                else:
+                    ptr = C.c_void_p()
+                    buf = (C.c_ubyte * _lib.XCHG_HANDLE_BYTES).from_buffer_copy(hb)
+                    _lib.check(lib.gssd_xchg_open(buf, C.byref(ptr)), "gssd_xchg_open")
+                    self.opened.append(ptr)
+                    x.peers[r] = ptr.value
+            self.x = x
+        except Exception as e:
+            self.error = e
 
     def close(self):
         for ptr in self.opened:
@@ -101,18 +113,17 @@ def peer_exchange(group=None):
     key = id(group) if group is not None else 0
     if key not in _exchanges:
         ex = None
-        try:
-            if dist.get_backend(group) == "nccl":
-                ex = PeerExchange(group)
-        except Exception as e:                                   # fall back to the all-gather, on every rank alike
-            import warnings
-            warnings.warn("gssd: peer exchange unavailable (%s); using the NCCL all-gather" % e)
-            ex = None
-        ok = torch.tensor([1 if ex is not None else 0], device="cuda")
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-        if int(ok) == 0 and ex is not None:
-            ex.close()
-            ex = None
+        if dist.get_backend(group) == "nccl":                    # the same answer on every rank
+            ex = PeerExchange(group)
+            if ex.error is not None:
+                import warnings
+                warnings.warn("gssd: peer exchange unavailable (%s); using the NCCL all-gather" % ex.error)
+            # every rank has mapped every buffer before first use, or nobody uses the exchange
+            ok = torch.tensor([1 if ex.error is None else 0], device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok) == 0:
+                ex.close()
+                ex = None
         _exchanges[key] = ex
     return _exchanges[key]
 

@@ -60,4 +60,32 @@ def test_pipeline_errors_mirror_the_reference():
     b = pipe.host_buffers()
     with pytest.raises(IndexError):
         pipe.submit(b, [torch.zeros(0, 5), torch.zeros(1, 5)])
+    # the C entry point checks the host-side row offsets itself (callers other than pipeline.py)
+    import ctypes as C
+    from grouped_ssd_pytorch_b200 import _lib
+    lib = _lib.load()
+    gt = torch.tensor([[0.1, 0.1, 0.5, 0.5, 0.0]] * 3).pin_memory()
+    b.loc.zero_(); b.conf.zero_(); b.scores.zero_()
+
+    def submit(off, sum_g, g_max):
+        o = torch.tensor(off, dtype=torch.int32).pin_memory()
+        return lib.gssd_pipe_submit(pipe._h, b.loc.data_ptr(), b.conf.data_ptr(), b.scores.data_ptr(), gt.data_ptr(), o.data_ptr(),
+                                    sum_g, g_max, b.losses.data_ptr(), b.detections.data_ptr())
+    assert submit([0, 1, 2], 3, 2) == _lib.ERR_ARG            # offsets do not end at sum_g
+    assert submit([0, 3, 3], 3, 3) == _lib.ERR_EMPTY          # image without ground truth
+    assert submit([0, 2, 3], 3, 1) == _lib.ERR_ARG            # more rows in an image than g_max
+    assert submit([1, 2, 3], 3, 2) == _lib.ERR_ARG
+    t = submit([0, 2, 3], 3, 2)
+    assert t >= 0
+    pipe.wait(t)
+    # begin without finish: the slot cannot be taken again
+    st = C.c_void_p()
+    o = torch.tensor([0, 2, 3], dtype=torch.int32).pin_memory()
+    begin = lambda: lib.gssd_pipe_begin(pipe._h, b.loc.data_ptr(), b.conf.data_ptr(), b.scores.data_ptr(), gt.data_ptr(), o.data_ptr(),
+                                        3, 2, b.detections.data_ptr(), C.byref(st))
+    t1 = begin(); t2 = begin()
+    assert t1 >= 0 and t2 >= 0 and begin() == _lib.ERR_ARG
+    for t in (t1, t2):
+        assert lib.gssd_pipe_finish(pipe._h, t, None, 0, b.losses.data_ptr()) == 0
+    pipe.wait(t2)
     pipe.close()
