@@ -199,6 +199,11 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// split cluster barrier: arrive early (e.g. once the buffers other CTAs will write into are initialised), wait right before
+// the first access to another CTA's shared memory — which also guarantees that every CTA of the cluster is running
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 // streaming (read-once) loads: keep them out of L1
 __device__ __forceinline__ float4 ldg_stream(const float4 *p) { return __ldcs(p); }
 __device__ __forceinline__ float2 ldg_stream(const float2 *p) { return __ldcs(p); }

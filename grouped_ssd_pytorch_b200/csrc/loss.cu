@@ -8,8 +8,8 @@
 //            shared memory;
 //   select : radix select of the min(ratio*num_pos, P-1) largest keys (select.cuh) — replaces the two
 //            full sorts of multibox_loss.py:102-103;
-//   sweep 2: cross-entropy (torch log_softmax, row max) over pos|neg and d(loss_c)/d(conf), zeros
-//            elsewhere; conf is re-read from L1/L2;
+//   sweep 2: cross-entropy (torch log_softmax, row max) over pos|neg and d(loss_c)/d(conf); every other
+//            prior gets its zero gradients here (stores only); conf is re-read from L2;
 //   finish : per-CTA partial sums in double, the last CTA reduces them in a fixed order and divides
 //            by N (multibox_loss.py:117-119).
 #include "select.cuh"
@@ -57,6 +57,10 @@ __global__ void __launch_bounds__(LOSS_NT, 4) loss_kernel(LossArgs a) {
     const int G = a.gt_off[b + 1] - g0;
     const int C = C2 ? 2 : a.C;
 
+    if (CLUSTER) {                       // the select's receiving buffers are cleared long before any CTA of the image adds into them
+        radix_select_prepare<LOSS_NT>(&sel_s);
+        cluster_arrive();
+    }
     float *sgt = reinterpret_cast<float *>(smem_raw);                    // [G][5]
     uint32_t *keys = reinterpret_cast<uint32_t *>(sgt + 5 * ((G + 3) & ~3));
     for (int i = tid; i < 5 * G; i += LOSS_NT) sgt[i] = a.gt[5 * (size_t)g0 + i];
@@ -114,8 +118,9 @@ __global__ void __launch_bounds__(LOSS_NT, 4) loss_kernel(LossArgs a) {
     GSSD_PHASE(loss, 0, dbg);
 
     // ---- sweep 1 ---------------------------------------------------------------------------------
-    // U priors per thread per trip, loads first: tag (2 B) + conf row; every prior gets zeroed gradients
-    // here, the few selected ones are overwritten in sweep 2 by the same thread.
+    // U priors per thread per trip, loads first: tag (2 B) + conf row.  No gradient is stored here except d(loss_l)/d(loc) of
+    // the few positives: the cluster barriers of the select below start with a GPU-scope memory barrier (that is what
+    // barrier.cluster.arrive.release compiles to), which would wait for every store still in flight.
     uint32_t *posbits = keys + ((a.slice + 3) & ~3);             // one bit per local prior
     for (int i = tid; i < (n_local + 31) / 32; i += LOSS_NT) posbits[i] = 0;
     __syncthreads();
@@ -162,11 +167,7 @@ __global__ void __launch_bounds__(LOSS_NT, 4) loss_kernel(LossArgs a) {
                 acc_l += (double)l0 + (double)l1 + (double)l2 + (double)l3;
                 g4.x = __fdiv_rn(g4.x, n_f); g4.y = __fdiv_rn(g4.y, n_f); g4.z = __fdiv_rn(g4.z, n_f); g4.w = __fdiv_rn(g4.w, n_f);
             }
-            if (GRADS && ok) {
-                __stcs(&a.grad_loc[o], g4);
-                if (C2) __stcs(reinterpret_cast<float2 *>(a.grad_conf + o * 2), make_float2(0.f, 0.f));
-                else for (int c = 0; c < C; ++c) a.grad_conf[o * C + c] = 0.f;
-            }
+            if (GRADS && pos) __stcs(&a.grad_loc[o], g4);        // the zeros of everybody else are written in sweep 2
         }
     }
     __syncthreads();
@@ -177,7 +178,13 @@ __global__ void __launch_bounds__(LOSS_NT, 4) loss_kernel(LossArgs a) {
     if (k > a.P - 1) k = a.P - 1;
     const bool have_sel = k > 0;
     unsigned long long cut = ~0ull;
-    if (have_sel) cut = radix_select<LOSS_NT, CLUSTER>(keys, n_local, (uint32_t)p0, (uint32_t)k, true, &sel_s);
+    if (CLUSTER) cluster_wait();         // every CTA of the image is running and has cleared its buffers
+#ifdef GSSD_PHASE_TIMING
+    long long *sel_clk = dbg ? g_phase_clock_loss + 8 : nullptr;
+#else
+    long long *sel_clk = nullptr;
+#endif
+    if (have_sel) cut = radix_select<LOSS_NT, CLUSTER>(keys, n_local, (uint32_t)p0, (uint32_t)k, true, &sel_s, sel_clk);
 
     GSSD_PHASE(loss, 2, dbg);
     // ---- sweep 2: only pos | neg priors do any work -----------------------------------------------------
@@ -188,7 +195,14 @@ __global__ void __launch_bounds__(LOSS_NT, 4) loss_kernel(LossArgs a) {
         const bool neg = have_sel && sel_composite(keys[li], (uint32_t)p, true) >= cut;
         if (a.pos_mask) a.pos_mask[o] = pos;
         if (a.neg_mask) a.neg_mask[o] = neg;
-        if (!(pos || neg)) continue;
+        if (GRADS && !pos) __stcs(&a.grad_loc[o], make_float4(0.f, 0.f, 0.f, 0.f));
+        if (!(pos || neg)) {
+            if (GRADS) {
+                if (C2) __stcs(reinterpret_cast<float2 *>(a.grad_conf + o * 2), make_float2(0.f, 0.f));
+                else for (int c = 0; c < C; ++c) a.grad_conf[o * C + c] = 0.f;
+            }
+            continue;
+        }
         const float *row = a.conf + o * C;
         const int t = pos ? (int)__fadd_rn(sgt[5 * (a.tags[o] & 0x7fff) + 4], 1.f) : 0;
         if (C2) {

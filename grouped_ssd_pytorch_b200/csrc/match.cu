@@ -38,13 +38,14 @@ struct MatchArgs {
 
 // dynamic shared memory layout
 //   u64    sbest[G]   packed (IoU bits, ~prior) best prior per GT, this CTA's slice
+//   u64    sin[S][G]  the same from every CTA of the image, stored here by its owner (distributed shared memory)
 //   float4 sgt4[G]    GT boxes
 //   float  sarea[G], slabel[G]
 //   int    sbp[G]     best prior per GT over the whole image
 //   int    glist[G]   GT rows that can overlap this CTA's prior slice (ascending)
 //   u16    stag[slice]
-static size_t match_smem_bytes(int g_max, int slice) {
-    return (size_t)g_max * (8 + 16 + 4 + 4 + 4 + 4) + (size_t)slice * 2 + 32;
+static size_t match_smem_bytes(int g_max, int slice, int S) {
+    return (size_t)g_max * (8 + 16 + 4 + 4 + 4 + 4) + (size_t)(g_max + 1) * 8 * (S > 1 ? S : 0) + (size_t)slice * 2 + 32;
 }
 
 constexpr int MATCH_CULL_MIN_G = 8;       // below this the bounding-box pre-pass costs more than it saves
@@ -61,7 +62,9 @@ __global__ void __launch_bounds__(MATCH_NT, GSSD_MATCH_MIN_CTAS) match_kernel(Ma
     const int G = a.gt_off[b + 1] - g0;
 
     unsigned long long *sbest = reinterpret_cast<unsigned long long *>(smem_raw);     // 16-byte aligned first
-    float4 *sgt4 = reinterpret_cast<float4 *>(sbest + ((G + 1) & ~1));
+    const int Gp = (G + 1) & ~1;
+    unsigned long long *sin = sbest + Gp;                                             // [nranks][Gp], clusters only
+    float4 *sgt4 = reinterpret_cast<float4 *>(sin + (nranks > 1 ? nranks * Gp : 0));
     float *sarea = reinterpret_cast<float *>(sgt4 + G);
     float *slabel = sarea + G;
     int *sbp = reinterpret_cast<int *>(slabel + G);
@@ -73,6 +76,7 @@ __global__ void __launch_bounds__(MATCH_NT, GSSD_MATCH_MIN_CTAS) match_kernel(Ma
     __shared__ int s_nlist;
     __shared__ bool s_is_last;
 
+    if (nranks > 1) cluster_arrive();    // waited for right before the first store into another CTA's shared memory
     // conf-max pass: a contiguous slice per CTA (uniform, streaming work)
     const int p0 = rank * a.slice;
     const int p1 = min(a.P, p0 + a.slice);
@@ -243,15 +247,19 @@ __global__ void __launch_bounds__(MATCH_NT, GSSD_MATCH_MIN_CTAS) match_kernel(Ma
 
     // ---- best prior per GT over the whole image, then the sequential force match -------------------
     if (nranks > 1) {
-        cluster.sync();
-        // one thread per (GT row, peer CTA): the remote reads of the per-slice maxima go out together instead of one
-        // distributed-shared-memory round trip after the other
+        // every CTA stores its per-slice maxima into its own row of every other CTA's `sin`: plain remote stores that need no
+        // answer, one barrier, and nothing is read remotely afterwards — no CTA has to outlive another
+        cluster_wait();                                              // all CTAs of the image are running
         for (unsigned i = tid; i < (unsigned)G * nranks; i += MATCH_NT) {
             const unsigned g = i / nranks, r = i - g * nranks;
-            if (r != rank) {
-                const unsigned long long o = cluster.map_shared_rank(sbest, r)[g];
-                if (o > sbest[g]) atomicMax(&sbest[g], o);
-            }
+            if (r != rank) cluster.map_shared_rank(sin, r)[rank * Gp + g] = sbest[g];
+        }
+        cluster.sync();
+        for (int g = tid; g < G; g += MATCH_NT) {
+            unsigned long long m = sbest[g];
+            for (unsigned r = 0; r < nranks; ++r)
+                if (r != rank) m = max(m, sin[r * Gp + g]);
+            sbest[g] = m;
         }
         __syncthreads();
     }
@@ -327,7 +335,6 @@ __global__ void __launch_bounds__(MATCH_NT, GSSD_MATCH_MIN_CTAS) match_kernel(Ma
         }
     }
     GSSD_PHASE(match, 3, dbg);
-    if (nranks > 1) cluster.sync();     // keep sbest alive until every CTA of the image has read it
     GSSD_PHASE(match, 4, dbg);
 }
 
@@ -339,7 +346,7 @@ static int launch_match(const MatchArgs &a_in, int B, int g_max, cudaStream_t st
     const int S = pick_cluster_size(GSSD_KERNEL_MATCH, B, a.P);
     a.slice = ceil_div(a.P, S);
     a.S = S;
-    size_t smem = match_smem_bytes(g_max, ceil_div(ceil_div(a.P, MATCH_NT), S) * MATCH_NT);
+    size_t smem = match_smem_bytes(g_max, ceil_div(ceil_div(a.P, MATCH_NT), S) * MATCH_NT, S);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(S, B, 1);
     cfg.blockDim = dim3(MATCH_NT, 1, 1);

@@ -2,8 +2,10 @@
 // multibox_loss.py:102-106, and the full sort + slice of nms, box_utils.py:194-196).
 //
 // The keys of one image live in shared memory as order-preserving uint32 (f2ord), either in one CTA
-// or split in contiguous slices across the CTAs of a thread-block cluster; histograms are then
-// summed over distributed shared memory.  The result is the exact "k largest keys" set with a
+// or split in contiguous slices across the CTAs of a thread-block cluster; every CTA then PUSHES its
+// non-empty histogram bins into the totals of all CTAs of the image (distributed-shared-memory reductions
+// that need no answer), so that one cluster barrier per pass is all the waiting there is and nothing is
+// read remotely afterwards.  The result is the exact "k largest keys" set with a
 // deterministic rule for equal keys (lower index first or higher index first), expressed as one
 // 64-bit cut: an element is selected iff  composite(key, index) >= cut,  where
 //   composite = key << 32 | (low_first ? ~index : index).
@@ -16,8 +18,8 @@
 namespace gssd {
 
 struct SelectShared {
-    uint32_t hist[2][256];   // double-buffered so that one cluster.sync per pass is enough
-    uint32_t total[256];
+    uint32_t hist[2][256];   // this CTA's bins (double-buffered: the last pass is read again when equal keys straddle the cut)
+    uint32_t total[2][256];  // cluster: bins of the whole image, added to by every CTA of the cluster (double-buffered per pass)
     uint32_t warp_tmp[32];
     uint32_t digit, k_rem, eq_total, eq_local_before;
     uint32_t fin_count;
@@ -35,6 +37,14 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
     return ((unsigned long long)hi << 32) | lo;
 }
 
+// cluster variant of radix_select: call at kernel start, all threads; then cluster_arrive() (any time later) and cluster_wait()
+// before radix_select, so that no CTA adds into totals that their owner has not cleared yet
+template <int NT>
+__device__ __forceinline__ void radix_select_prepare(SelectShared *s) {
+    for (int i = threadIdx.x; i < 512; i += NT) (&s->total[0][0])[i] = 0;
+    if (threadIdx.x == 0) s->fin_count = 0;
+}
+
 // compare-exchange half: keep the larger (keep_max) or the smaller of (mine, other)
 __device__ __forceinline__ void cmpx(unsigned long long &mine, unsigned long long other, bool keep_max) {
     if ((other > mine) == keep_max) mine = other;
@@ -42,24 +52,31 @@ __device__ __forceinline__ void cmpx(unsigned long long &mine, unsigned long lon
 
 // NT threads per CTA (multiple of 32, >= 256).  keys[0..n_local) are this CTA's slice, whose first
 // element has image-wide index `index_base`.  1 <= k <= number of keys in the image.
-// CLUSTER: slices are ordered by cluster rank.  Returns the cut (may differ between the CTAs of an
-// image, each value classifies that CTA's own elements correctly).
+// CLUSTER: slices are ordered by cluster rank; radix_select_prepare + a cluster barrier must have happened.  Returns the
+// cut (may differ between the CTAs of an image, each value classifies that CTA's own elements correctly).
 template <int NT, bool CLUSTER>
 __device__ unsigned long long radix_select(const uint32_t *keys, int n_local, uint32_t index_base, uint32_t k,
-                                           bool low_first, SelectShared *s) {
+                                           bool low_first, SelectShared *s, long long *dbg_clk = nullptr) {
+    // debug build only (tools/phase_times.py): clock stamps of thread 0, four per pass + two for the final ranking
+#define SEL_STAMP(i) do { if (dbg_clk && threadIdx.x == 0) dbg_clk[i] = clock64(); } while (0)
+    int stamp = 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned nranks = CLUSTER ? cluster.num_blocks() : 1;
     const unsigned rank = CLUSTER ? cluster.block_rank() : 0;
     const int n_round = (n_local + NT - 1) / NT * NT;
 
-    if (tid == 0) s->fin_count = 0;
+    if (!CLUSTER && tid == 0) s->fin_count = 0;
     uint32_t prefix = 0, mask = 0, k_rem = k, eq_total = 0;
     int buf = 0;
 #pragma unroll 1
     for (int shift = 24; shift >= 0; shift -= 8, buf ^= 1) {
-        for (int i = tid; i < 256; i += NT) s->hist[buf][i] = 0;
+        for (int i = tid; i < 256; i += NT) {
+            s->hist[buf][i] = 0;
+            if (CLUSTER) s->total[buf ^ 1][i] = 0;               // the next pass adds into it, after this pass's barrier
+        }
         __syncthreads();
+        SEL_STAMP(stamp++);
         for (int i = tid; i < n_round; i += NT) {
             bool in = i < n_local;
             const uint32_t key = in ? keys[i] : 0;
@@ -72,24 +89,20 @@ __device__ unsigned long long radix_select(const uint32_t *keys, int n_local, ui
             }
         }
         __syncthreads();
+        SEL_STAMP(stamp++);
         const uint32_t *tot = s->hist[buf];
         if (CLUSTER) {
-            cluster.sync();
+            // push the non-empty bins into every CTA's totals (mine included): reductions without a return value, in flight
+            // while the other CTAs of the image are still counting
             for (int i = tid; i < 256; i += NT) {
-                // the (up to 8) remote reads are independent: unrolled so that they are in flight together instead of one
-                // distributed-shared-memory round trip after the other
-                uint32_t part[8];
-#pragma unroll
-                for (unsigned r = 0; r < 8; ++r) part[r] = r < nranks ? cluster.map_shared_rank(&s->hist[buf][0], r)[i] : 0u;
-                uint32_t t = 0;
-#pragma unroll
-                for (unsigned r = 0; r < 8; ++r) t += part[r];
-                for (unsigned r = 8; r < nranks; ++r) t += cluster.map_shared_rank(&s->hist[buf][0], r)[i];
-                s->total[i] = t;
+                const uint32_t c = s->hist[buf][i];
+                if (c)
+                    for (unsigned r = 0; r < nranks; ++r) atomicAdd(&cluster.map_shared_rank(&s->total[buf][0], r)[i], c);
             }
-            tot = s->total;
-            __syncthreads();
+            cluster.sync();
+            tot = s->total[buf];
         }
+        SEL_STAMP(stamp++);
         // suffix sums over the 256 bins (bin 255 first): the first 8 warps own one bin per thread
         if (tid < 256) {
             const uint32_t c = tot[tid];
@@ -109,6 +122,7 @@ __device__ unsigned long long radix_select(const uint32_t *keys, int n_local, ui
             }
         }
         __syncthreads();
+        SEL_STAMP(stamp++);
         prefix |= s->digit << shift;
         mask |= 255u << shift;
         k_rem = s->k_rem;
@@ -117,18 +131,26 @@ __device__ unsigned long long radix_select(const uint32_t *keys, int n_local, ui
     }
 
     if (eq_total <= 32u) {
-        // ---- gather the members of the bin into rank 0's list and rank them with one warp -------------
-        SelectShared *s0 = CLUSTER ? cluster.map_shared_rank(s, 0) : s;
+        // ---- gather the members of the bin and rank them with one warp; in a cluster every CTA receives every member
+        // (<= 32 of them), so that nothing is read remotely after the barrier and no CTA has to outlive another ---------
         for (int i = tid; i < n_local; i += NT) {
             const uint32_t key = keys[i];
             if ((key & mask) == prefix) {
-                const uint32_t slot = atomicAdd(&s0->fin_count, 1u);
-                s0->fin_list[slot] = sel_composite(key, index_base + (uint32_t)i, low_first);
+                const unsigned long long comp = sel_composite(key, index_base + (uint32_t)i, low_first);
+                if (CLUSTER) {
+                    for (unsigned r = 0; r < nranks; ++r) {
+                        SelectShared *sr = cluster.map_shared_rank(s, r);
+                        sr->fin_list[atomicAdd(&sr->fin_count, 1u)] = comp;
+                    }
+                } else {
+                    s->fin_list[atomicAdd(&s->fin_count, 1u)] = comp;
+                }
             }
         }
         if (CLUSTER) cluster.sync(); else __syncthreads();
+        SEL_STAMP(stamp++);
         if (warp == 0) {
-            unsigned long long c = lane < (int)eq_total ? s0->fin_list[lane] : 0ull;
+            unsigned long long c = lane < (int)eq_total ? s->fin_list[lane] : 0ull;
 #pragma unroll
             for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
@@ -142,9 +164,8 @@ __device__ unsigned long long radix_select(const uint32_t *keys, int n_local, ui
             if (lane == 0) s->cut = c;
         }
         __syncthreads();
-        const unsigned long long cut = s->cut;
-        if (CLUSTER) cluster.sync();         // rank 0's list / everybody's histograms stay alive until here
-        return cut;
+        SEL_STAMP(stamp++);
+        return s->cut;
     }
 
     // ---- all 32 bits resolved and more than 32 keys are exactly equal to v = prefix -----------------------
@@ -196,6 +217,7 @@ __device__ unsigned long long radix_select(const uint32_t *keys, int n_local, ui
     }
     __syncthreads();
     return sel_composite(v, index_base + (uint32_t)s->tie_idx, low_first);
+#undef SEL_STAMP
 }
 
 }  // namespace gssd

@@ -20,3 +20,6 @@ for args in (["32", "v2", "5", "2"], ["256", "v2", "5", "2"], ["1024", "v2", "5"
         d = [t[i + 1] - t[i] for i in range(len(labels))]
         print("B=%s %s %-7s total %7d cyc: " % (args[0], args[1], name, t[len(labels)] - t[0]) +
               "  ".join("%s=%d" % (l, x) for l, x in zip(labels, d)), flush=True)
+        if name == "loss":     # stamps inside the select: [zeroed, counted, pushed+barrier, suffix] per pass, then [gathered+barrier, ranked]
+            sel = [x for x in t[8:24] if x > 0]
+            print("      select stamps (cycles after sweep 1): " + " ".join(str(x - t[1]) for x in sel), flush=True)
