@@ -15,7 +15,7 @@ dev = torch.device("cuda:0")
 HBM = 6521.4
 
 
-def timeit(fn, n_sets, iters=20, warm=3):
+def timeit(fn, n_sets, iters=int(os.environ.get("QP_ITERS", "20")), warm=3):
     for i in range(warm):
         fn(i % n_sets)
     torch.cuda.synchronize()
@@ -68,5 +68,9 @@ def run(pname, B, gmax):
 
 
 if __name__ == "__main__":
+    if os.environ.get("QP_ONLY"):             # one configuration, several repeats (A/B runs of library variants)
+        for _ in range(3):
+            run("v2", int(os.environ["QP_ONLY"]), 5)
+        sys.exit(0)
     for pname, B, g in [("v2", 32, 5), ("v2", 64, 5), ("v2", 256, 5), ("v2", 1024, 5), ("v2_512", 64, 32), ("v2_512", 512, 32)]:
         run(pname, B, g)
