@@ -329,7 +329,10 @@ GSSD_API void    gssd_pipe_destroy(gssd_pipe *p);
 GSSD_API int     gssd_pipe_slot_info(const gssd_pipe *p, int slot, gssd_pipe_slot *out_host);
 /* Enqueue one step.  Returns its ticket (>= 0; slot = ticket % depth) or a negative GSSD_ERR_* / -(1000 + cudaError_t).
  * Blocks only when all `depth` slots are in flight (it then waits for the oldest step).  gt_host[sum_g,5] /
- * gt_off_host[B+1] are the packed ground truth.  losses_host[2], detect_out_host[B,C,top_k,5]. */
+ * gt_off_host[B+1] are the packed ground truth.  losses_host[2], detect_out_host[B,C,top_k,5].
+ * The row offsets are checked on the host before anything is enqueued: gt_off_host[0] == 0, gt_off_host[B] == sum_g, every
+ * image has between 1 and g_max rows (GSSD_ERR_EMPTY for an image without ground truth — the reference raises IndexError,
+ * box_utils.py:94 — GSSD_ERR_ARG otherwise); GSSD_ERR_ARG too when the slot's previous gssd_pipe_begin was never finished. */
 GSSD_API int64_t gssd_pipe_submit(gssd_pipe *p, const float *loc_host, const float *conf_host, const float *scores_host,
                          const float *gt_host, const int32_t *gt_off_host, int sum_g, int g_max,
                          float *losses_host, float *detect_out_host);
