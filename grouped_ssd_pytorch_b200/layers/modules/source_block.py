@@ -190,6 +190,17 @@ class _Conv(object):
         self.shift = (_lib.f32(bn.bias, dev) + (self.bias - _lib.f32(bn.running_mean, dev)) * s).contiguous()
 
 
+def dgrad_weight(weight, groups):
+    """Filter with which the data gradient of a stride-1 'same' convolution is itself such a convolution of dY:
+    d/dx conv2d(x, w, padding=k//2, groups=g) . dY == conv2d(dY, dgrad_weight(w, g), padding=k//2, groups=g) —
+    rotated by 180 degrees, in / out channels swapped inside each group ([Cout, Cin/g, k, k] -> [Cin, Cout/g, k, k]).
+    Host-side half of the backward planned in DESIGN.md §7: packed with `gssd_conv_pack_weights`, it puts dgrad on the
+    same tcgen05 kernel as the forward."""
+    cout, cin_g, kh, kw = weight.shape
+    wt = weight.reshape(groups, cout // groups, cin_g, kh, kw).transpose(1, 2).flip(3, 4)
+    return wt.reshape(groups * cin_g, cout // groups, kh, kw).contiguous()
+
+
 def conv_igemm(x, cv, relu, y=True, row_ss_in=None, l2_eps=1e-10, row_ss_out=None, chan_sum=None, scale=None, shift=None,
                head=None):
     """One `gssd_conv_igemm` call.  x: PM; cv: _Conv; head = (loc, conf, n_anchor, n_cls, prior_off, n_priors)."""
