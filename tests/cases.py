@@ -135,3 +135,10 @@ def block_case(tag):
     conv(A * 4, Cf, 3, "loc")
     conv(A * ncls, Cf, 3, "conf")
     return x, prm, training
+
+
+def block_upstream(tag, n_loc, n_conf):
+    """seeded upstream gradients (d_loc[N, n_loc], d_conf[N, n_conf]) of a source-block case, float64"""
+    seed, N = BLOCK_CASES[tag][0], BLOCK_CASES[tag][1]
+    r = np.random.RandomState(seed + 1000)
+    return r.randn(N, n_loc), r.randn(N, n_conf)
