@@ -4,22 +4,31 @@
     python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
 
-A step = one pass of the hot path over one batch: MultiBoxLoss forward + backward (2 kernels + the
-backward rescale) and Detect (1 kernel) on `--batch` images per GPU (BASELINE.json configs[1]:
-batch 32, SSD300 priors P=8732, 1-5 GT boxes per image, C=2).  Weak scaling: the per-GPU batch is
-fixed; every rank owns its own images, the only exchange is the 16 bytes of loss statistics per rank, stored
-into the peers' memory over NVLink by the last CTA of the match kernel (no collective call).
+A step = one pass of the hot path over one batch.  `--config` picks the BASELINE.json workload:
+  1 (default) configs[1]: MultiBoxLoss forward + backward and Detect on 32 images per GPU, SSD300 priors (P=8732),
+              1-5 GT boxes per image, C=2.  Weak scaling (the per-GPU batch is fixed).
+  3           configs[3]: Detect/NMS only, global batch 256 sharded over the N GPUs (strong scaling), conf_thresh 0.2,
+              top_k 200, nms 0.45.
+  4           configs[4]: matching + OHNM loss forward + backward only, SSD512 priors (P=24564), up to 32 GT boxes per
+              image, global batch 512 sharded over the N GPUs (strong scaling).
+Every rank owns its own images; the only exchange is the 16 bytes of loss statistics per rank, stored into the peers'
+memory over NVLink by the kernels themselves (no collective call).  At N > 1 rank 0 also gathers the global batch once,
+runs it through the single-GPU path and asserts that the sharded result is the same (`parity_check` in the JSON line).
 
 value : inputs resident in HBM, a ring of input sets larger than L2, CUDA-graph replay of the public
         API calls, CUDA-event timing, max over ranks.
-e2e   : the same step through the public Python API from pinned HOST buffers: H2D of loc / conf /
-        scores / targets, kernels, D2H of the two losses and of the Detect output, every step.
+e2e   : the same step through the reference-facing host-buffer call (gssd_pipe_submit) from pinned HOST buffers: H2D of
+        loc / conf / targets, kernels, D2H of the two losses and of the Detect output, every step.
+Both timed regions run a whole number of rounds of `--steps` steps, as many as it takes to reach `--min-seconds` (0.5 s),
+so that a short `--steps` cannot turn the number into a measurement of launch jitter; `steps` in the JSON line is what
+was timed.
 roofline: the dominant kernel, timed alone with CUDA events inside this run, against
         MEASURED_PEAKS.json (hbm_gbs).   cpu_baseline: the CPU oracle (port of the reference
         algorithm, OpenMP over images) on the box's host cores, bounded sample.
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -38,6 +47,11 @@ UNIT = "images/s"
 TOP_K, CONF_THRESH, NMS_THRESH, NEGPOS, MATCH_THRESH = 200, 0.2, 0.45, 3, 0.5
 CLASS_BIAS = (0.0, -4.0)        # Detect scores = softmax(conf + bias): the "sparse-realistic" shift of BASELINE.md §3 (~3 % of priors > 0.2)
 L2_BYTES = 126e6
+PRESETS = {
+    1: dict(mode="both", scaling="weak", batch=32, priors="v2", gmax=5),
+    3: dict(mode="detect", scaling="strong", global_batch=256, priors="v2", gmax=5),
+    4: dict(mode="loss", scaling="strong", global_batch=512, priors="v2_512", gmax=32),
+}
 
 
 def parse():
@@ -46,21 +60,49 @@ def parse():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="images per GPU (configs[1]: 32)")
-    ap.add_argument("--priors", default="v2", help="prior-box config (v2: P=8732, v2_512: P=24564)")
-    ap.add_argument("--gmax", type=int, default=5, help="GT boxes per image ~ U{1..gmax}")
+    ap.add_argument("--config", type=int, default=1, choices=sorted(PRESETS), help="BASELINE.json configs[i] preset")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (overrides the preset)")
+    ap.add_argument("--priors", default=None, help="prior-box config (v2: P=8732, v2_512: P=24564; overrides the preset)")
+    ap.add_argument("--gmax", type=int, default=None, help="GT boxes per image ~ U{1..gmax} (overrides the preset)")
+    ap.add_argument("--min-seconds", type=float, default=0.5, help="minimum duration of each timed region")
     ap.add_argument("--no-graph", action="store_true", help="time eager API calls instead of CUDA-graph replay")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gconv", action="store_true", help="skip the tensor-core source-block measurement")
-    ap.add_argument("--sweep", action="store_true", help="(default at N=1) also report the kernels' roofline at larger batches")
+    ap.add_argument("--sweep", action="store_true", help="(default at N=1, config 1) also report the kernels' roofline at larger batches")
     ap.add_argument("--no-sweep", action="store_true", help="skip the large-batch roofline sweep")
-    return ap.parse_args()
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the gathered-batch check against the single-GPU path")
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    resolve(a, max(1, max(world, a.gpus) if a.impl == "reference" else world))
+    return a
+
+
+def resolve(a, world):
+    """fill the workload fields from the preset; a.batch is PER GPU from here on"""
+    pre = PRESETS[a.config]
+    a.mode, a.scaling = pre["mode"], pre["scaling"]
+    a.priors = a.priors or pre["priors"]
+    a.gmax = a.gmax or pre["gmax"]
+    if a.batch is None:
+        a.batch = pre["batch"] if a.scaling == "weak" else max(1, pre["global_batch"] // world)
+    a.world = world
+    a.global_batch = a.batch * world
 
 
 def workload_name(a):
-    return "configs[1]: GSSD multibox head, batch %d/GPU, %s priors, 1-%d GT, C=2, loss fwd+bwd + Detect(thr %.1f, top_k %d, nms %.2f)" % (
-        a.batch, a.priors, a.gmax, CONF_THRESH, TOP_K, NMS_THRESH)
+    what = {"both": "loss fwd+bwd + Detect(thr %.1f, top_k %d, nms %.2f)" % (CONF_THRESH, TOP_K, NMS_THRESH),
+            "detect": "Detect only (thr %.1f, top_k %d, nms %.2f)" % (CONF_THRESH, TOP_K, NMS_THRESH),
+            "loss": "matching + OHNM loss fwd+bwd only"}[a.mode]
+    return "configs[%d]: GSSD multibox head, batch %d/GPU, %s priors, 1-%d GT, C=2, %s" % (a.config, a.batch, a.priors, a.gmax, what)
+
+
+def config_dict(a, P):
+    """the `config` object: identical (keys and values) in our arm and in the reference arm of the same command line"""
+    return {"workload": workload_name(a), "preset": a.config, "mode": a.mode, "batch_per_gpu": a.batch,
+            "global_batch": a.global_batch, "num_priors": P, "num_classes": 2, "gt_per_image": "U{1..%d}" % a.gmax,
+            "parallelism": "dp%d" % a.world, "scaling": a.scaling,
+            "l2_policy": "ring of distinct input sets larger than L2 (126 MB)"}
 
 
 def peaks():
@@ -81,21 +123,42 @@ def make_inputs(a, rank, n_sets):
         tg = syn.targets(r, a.batch, 1, a.gmax)
         loc = syn.loc(r, a.batch, a.P)
         conf = syn.conf_logits(r, a.batch, a.P, 2)
-        x = conf.copy()
-        x[..., 1] -= 4.0                                  # "sparse-realistic" Detect scores
-        sets.append(dict(targets=tg, loc=loc, conf=conf, scores=syn.softmax(x)))
+        sets.append(dict(targets=tg, loc=loc, conf=conf))
     return sets
+
+
+def detect_scores(conf):
+    """softmax(conf + CLASS_BIAS): the "sparse-realistic" Detect scores the CPU arm reads precomputed"""
+    from grouped_ssd_pytorch_b200 import synthetic as syn
+    x = conf.copy()
+    x[..., 0] += np.float32(CLASS_BIAS[0]); x[..., 1] += np.float32(CLASS_BIAS[1])
+    return syn.softmax(x)
 
 
 # ------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference algorithm on the host cores
+def cpu_threads():
+    """all the host threads this process may use (cgroup / affinity aware), set explicitly: torchrun exports
+    OMP_NUM_THREADS=1, which would silently make the oracle single-threaded"""
+    from oracle import oracle as O
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return O.set_threads(n)
+
+
 def cpu_step_fn(a, priors_np):
     from oracle import oracle as O
     O.lib()
 
     def step(s):
-        O.multibox_loss(s["loc"], s["conf"], priors_np, s["targets"], MATCH_THRESH, NEGPOS, (0.1, 0.2), grads=True, extras=False)
-        O.detect(s["loc"], s["scores"], priors_np, 2, TOP_K, CONF_THRESH, NMS_THRESH, (0.1, 0.2))
+        if a.mode in ("both", "loss"):
+            O.multibox_loss(s["loc"], s["conf"], priors_np, s["targets"], MATCH_THRESH, NEGPOS, (0.1, 0.2), grads=True, extras=False)
+        if a.mode in ("both", "detect"):
+            if "scores" not in s:
+                s["scores"] = detect_scores(s["conf"])
+            O.detect(s["loc"], s["scores"], priors_np, 2, TOP_K, CONF_THRESH, NMS_THRESH, (0.1, 0.2))
     return step
 
 
@@ -114,6 +177,11 @@ def time_cpu(a, priors_np, sets, steps, warmup, budget_s):
     return done, dt
 
 
+def cpu_sample_text(a, done, dt):
+    what = {"both": "loss fwd+bwd + Detect", "detect": "Detect", "loss": "loss fwd+bwd"}[a.mode]
+    return "%d steps of the batch-%d workload (%s) in %.1f s (oracle/gssd_oracle.c, OpenMP over images)" % (done, a.batch, what, dt)
+
+
 def run_reference(a):
     """--impl reference: the reference algorithm (CPU oracle port, all host threads) on our config."""
     rank = int(os.environ.get("RANK", "0"))
@@ -123,19 +191,20 @@ def run_reference(a):
     from oracle import oracle as O
     priors_np = O.priorbox(config.ALL[a.priors])
     a.P = priors_np.shape[0]
-    sets = make_inputs(a, 0, 4)
-    cores = os.cpu_count() or 1
-    done, dt = time_cpu(a, priors_np, sets, a.steps, min(a.warmup, 3), budget_s=120.0)
+    sets = make_inputs(a, 0, 4 if a.batch * a.P < 4e6 else 2)
+    threads = cpu_threads()
+    done, dt = time_cpu(a, priors_np, sets, a.steps, min(a.warmup, 3), budget_s=60.0)
     v = done * a.batch / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": done,
-        "warmup": a.warmup, "ms_per_step": dt / done * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": a.warmup, "ms_per_step": dt / done * 1e3, "higher_is_better": True, "scaling": a.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "batch_per_gpu": a.batch, "num_priors": a.P,
-                   "note": "reference algorithm as the CPU oracle port (oracle/gssd_oracle.c, OpenMP over images); "
-                           "the reference itself is Python/torch and is not present on the GPU box"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d steps of the batch-%d workload (loss fwd+bwd + Detect)" % (done, a.batch)},
+        "config": config_dict(a, a.P),
+        "details": {"note": "reference algorithm as the CPU oracle port (oracle/gssd_oracle.c, OpenMP over images) on the host "
+                            "cores of the box; the reference itself is Python/torch and is not present on the GPU box. "
+                            "Each step is one batch_per_gpu-sized batch of the workload (a bounded sample)",
+                    "omp_threads": threads, "os_cpu_count": os.cpu_count()},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample_text(a, done, dt)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -199,6 +268,106 @@ def dbg(msg):
         sys.stderr.flush()
 
 
+def pin_to_gpu_numa(torch, local):
+    """bind this rank's host threads (and therefore its page-locked buffers, first touch) to the CPUs next to its GPU:
+    at N = 8 the ranks otherwise share whichever socket the launcher started them on.  Returns a description."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open(path) as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            return "cpus %s (local to the GPU)" % txt
+        return "unchanged (%d cpus allowed, GPU-local list %s)" % (len(allowed), txt)
+    except Exception as e:                                       # pragma: no cover
+        return "unavailable (%s)" % type(e).__name__
+
+
+def nrank_parity(a, torch, dist, dev, rank, world, priors, dsets, MultiBoxLoss, Detect):
+    """N > 1: the reference computes the loss on the DataParallel-gathered global batch (train_lesion_multiphase_v2.py:242-246
+    -> multibox_loss.py:117, box_utils.py:167).  Every rank runs its shard of input set 0 through the sharded path (statistics
+    exchanged between the ranks); rank 0 gathers inputs and results, runs the whole batch through the single-GPU path and
+    compares: sum over ranks of the losses within 1e-6 relative, positive / hard-negative masks and Detect output bit-equal."""
+    d = dsets[0]
+    res = {"checked": False}
+    out_l = {}
+    if a.mode in ("both", "loss"):
+        crit = MultiBoxLoss(2, MATCH_THRESH, True, 0, True, NEGPOS, 0.5, False, True)
+        crit.keep_masks = True
+        loc = d["loc"].detach().clone().requires_grad_()
+        conf = d["conf"].detach().clone().requires_grad_()
+        ll, lc = crit((loc, conf, priors), d["targets"])
+        (ll + lc).backward()
+        out_l = dict(losses=torch.stack([ll.detach(), lc.detach()]), pos=crit.last_masks["pos"].clone(),
+                     neg=crit.last_masks["neg"].clone(), gl=loc.grad, gc=conf.grad)
+    det = None
+    if a.mode in ("both", "detect"):
+        det = Detect.apply_logits(2, 0, TOP_K, CONF_THRESH, NMS_THRESH, d["loc"].detach(), d["conf"].detach(), priors, class_bias=CLASS_BIAS)
+    torch.cuda.synchronize()
+
+    def gather(t):
+        bufs = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+        dist.gather(t.contiguous(), bufs, dst=0)
+        return bufs
+
+    g_loc, g_conf = gather(d["loc"].detach()), gather(d["conf"].detach())
+    gt, gt_off = d["targets"][0], d["targets"][1]
+    # packed ground truth: rows differ per rank -> pad to the global maximum
+    n_rows = torch.tensor([gt.shape[0]], device=dev)
+    all_rows = [torch.zeros_like(n_rows) for _ in range(world)]
+    dist.all_gather(all_rows, n_rows)
+    max_rows = int(max(int(x) for x in all_rows))
+    gt_pad = torch.zeros((max_rows, 5), device=dev); gt_pad[:gt.shape[0]] = gt
+    g_gt, g_off = gather(gt_pad), gather(gt_off)
+    g_out = {k: gather(v) for k, v in out_l.items()}
+    g_det = gather(det) if det is not None else None
+    if rank == 0:
+        from grouped_ssd_pytorch_b200.layers.box_utils import pack_target_list
+        LOC, CONF = torch.cat(g_loc), torch.cat(g_conf)
+        tg = []
+        for r in range(world):
+            off = g_off[r].cpu().tolist()
+            tg += [g_gt[r][off[i]:off[i + 1]] for i in range(len(off) - 1)]
+        res = {"checked": True, "global_batch": int(LOC.shape[0])}
+        if out_l:
+            crit1 = MultiBoxLoss(2, MATCH_THRESH, True, 0, True, NEGPOS, 0.5, False, True)
+            crit1.process_group = False                          # single-GPU path: statistics of the whole batch, no exchange
+            crit1.keep_masks = True
+            L1, C1 = LOC.clone().requires_grad_(), CONF.clone().requires_grad_()
+            ll1, lc1 = crit1((L1, C1, priors), pack_target_list(tg, dev))
+            (ll1 + lc1).backward()
+            tot = torch.stack(g_out["losses"]).double().sum(0)
+            ref = torch.stack([ll1.detach(), lc1.detach()]).double()
+            rel = ((tot - ref).abs() / ref.abs()).max().item()
+            pos_eq = bool(torch.equal(torch.cat(g_out["pos"]), crit1.last_masks["pos"]))
+            neg_eq = bool(torch.equal(torch.cat(g_out["neg"]), crit1.last_masks["neg"]))
+            g_err = max((torch.cat(g_out["gl"]) - L1.grad).abs().max().item(), (torch.cat(g_out["gc"]) - C1.grad).abs().max().item())
+            g_scale = max(L1.grad.abs().max().item(), C1.grad.abs().max().item())
+            res.update(loss_rel_err=rel, pos_mask_equal=pos_eq, neg_mask_equal=neg_eq, grad_max_abs_err=g_err, grad_scale=g_scale,
+                       num_pos=int(crit1.last_masks["num_pos"].sum().item()))
+            assert rel <= 1e-6, "N-rank loss differs from the single-GPU loss of the gathered batch: rel %.3e" % rel
+            assert pos_eq and neg_eq, "N-rank positive / hard-negative masks differ from the single-GPU path"
+            assert g_err <= 1e-6 * g_scale + 1e-12, "N-rank gradients differ from the single-GPU path"
+        if g_det is not None:
+            det1 = Detect.apply_logits(2, 0, TOP_K, CONF_THRESH, NMS_THRESH, LOC, CONF, priors, class_bias=CLASS_BIAS)
+            det_eq = bool(torch.equal(torch.cat(g_det), det1))
+            res.update(detect_equal=det_eq)
+            assert det_eq, "N-rank Detect output differs from the single-GPU path"
+        torch.cuda.synchronize()
+    dist.barrier()
+    return res
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -213,15 +382,17 @@ def run_ours(a):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa(torch, local) if world > 1 else "not applied (1 rank)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.require_cuda()
     dbg('init done')
+    do_loss, do_det = a.mode in ("both", "loss"), a.mode in ("both", "detect")
 
     priors = PriorBox(config.ALL[a.priors]).forward(device="cuda")
     a.P = P = priors.shape[0]
     B = a.batch
-    per_set = B * P * (16 + 8 + 8 + 16 + 8)              # loc, conf, scores, grad_loc, grad_conf
+    per_set = B * P * ((16 + 8) + (16 + 8 if do_loss else 0))   # loc, conf (+ grad_loc, grad_conf)
     n_sets = int(min(64, max(2, L2_BYTES * 1.5 // per_set + 1)))
     host = make_inputs(a, rank, n_sets)
 
@@ -230,7 +401,6 @@ def run_ours(a):
     for s in host:
         dsets.append(dict(loc=torch.from_numpy(s["loc"]).to(dev).requires_grad_(),
                           conf=torch.from_numpy(s["conf"]).to(dev).requires_grad_(),
-                          scores=torch.from_numpy(s["scores"]).to(dev),
                           # ground truth resident in HBM in its packed form (gt[sum_G,5] + row offsets): the device image
                           # of the reference's `targets` list; MultiBoxLoss takes it as is (the e2e arm packs host lists)
                           targets=pack_targets([torch.from_numpy(t) for t in s["targets"]], dev)))
@@ -239,14 +409,21 @@ def run_ours(a):
 
     def step_device(d):
         main = torch.cuda.current_stream()
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
+        out = ll = lc = None
+        if do_det and do_loss:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                out = Detect.apply_logits(2, 0, TOP_K, CONF_THRESH, NMS_THRESH, d["loc"].detach(), d["conf"].detach(), priors,
+                                          class_bias=CLASS_BIAS)
+        elif do_det:
             out = Detect.apply_logits(2, 0, TOP_K, CONF_THRESH, NMS_THRESH, d["loc"].detach(), d["conf"].detach(), priors,
                                       class_bias=CLASS_BIAS)
-        d["loc"].grad = None; d["conf"].grad = None
-        ll, lc = crit((d["loc"], d["conf"], priors), d["targets"])
-        (ll + lc).backward()
-        main.wait_stream(side)
+        if do_loss:
+            d["loc"].grad = None; d["conf"].grad = None
+            ll, lc = crit((d["loc"], d["conf"], priors), d["targets"])
+            (ll + lc).backward()
+        if do_det and do_loss:
+            main.wait_stream(side)
         return ll, lc, out
 
     # ---- kernels per step + optional CUDA graphs -------------------------------------------------------
@@ -258,6 +435,12 @@ def run_ours(a):
     torch.cuda.synchronize()
     kernels_per_step = _lib.launch_count() - n0
     dbg('eager steps ok, kernels/step=%d' % kernels_per_step)
+
+    # ---- N > 1: the sharded step against the single-GPU path on the gathered batch ---------------------------
+    parity = None
+    if world > 1 and not a.no_parity_check:
+        parity = nrank_parity(a, torch, dist, dev, rank, world, priors, dsets, MultiBoxLoss, Detect)
+        dbg('parity check done: %s' % parity)
 
     graphs, use_graph = None, not a.no_graph
     if use_graph:
@@ -295,39 +478,52 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def agree_max(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
     # ---- timed region: device-resident --------------------------------------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
     # W warm-up steps, then more in chunks until >= 0.5 s have passed so that the clocks have ramped; the
-    # ranks agree on every extra chunk (the steps contain a collective, so the counts must match)
+    # ranks agree on every extra chunk (the steps contain an exchange, so the counts must match)
+    K = max(1, a.steps)
     t_w = time.perf_counter()
     for i in range(max(3, a.warmup)):
         run_step(i)
     for _ in range(200):
         torch.cuda.synchronize()
-        more = torch.tensor([1.0 if time.perf_counter() - t_w < 0.5 else 0.0], device=dev)
-        if world > 1:
-            dist.all_reduce(more, op=dist.ReduceOp.MAX)
-        if float(more) == 0.0:
+        if agree_max(1.0 if time.perf_counter() - t_w < 0.5 else 0.0) == 0.0:
             break
         for i in range(64):
             run_step(i)
+    # one untimed round of K steps sizes the timed region: whole rounds of K steps, at least --min-seconds of them
     barrier()
-    dbg('warm-up done')
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        run_step(i)
+    e1.record()
+    barrier()
+    round_ms = agree_max(e0.elapsed_time(e1))
+    rounds = int(max(1, min(10000, math.ceil(a.min_seconds * 1e3 / max(round_ms, 1e-3)))))
+    steps = rounds * K
+    dbg('warm-up done; %d rounds of %d steps' % (rounds, K))
     n_launch0 = _lib.launch_count()
     e0.record()
-    for i in range(a.steps):
+    for i in range(steps):
         run_step(i)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     dbg('timed region done')
     eager_launches = _lib.launch_count() - n_launch0
-    gpu_launches = kernels_per_step * a.steps if graphs is not None else eager_launches
+    gpu_launches = kernels_per_step * steps if graphs is not None else eager_launches
 
     # ---- end to end: host buffers in, losses + detections out, every step -----------------------------------
     # The reference-facing host-buffer call (include/gssd.h gssd_pipe_*, grouped_ssd_pytorch_b200/pipeline.py): one
-    # native call per step copies that step's loc / conf / scores / targets from page-locked host memory to the device,
+    # native call per step copies that step's loc / conf / targets from page-locked host memory to the device,
     # runs match + loss (with gradients) + Detect, and copies the two losses and the Detect tensor back; 3 steps are in
     # flight so that step i's H2D runs beside step i-1's kernels and D2H.  The host waits for a step's results before it
     # reuses that step's buffers, and every step's copies are inside the timed region.
@@ -342,7 +538,7 @@ def run_ours(a):
         hb = pipe.host_buffers()
         src = host[i % n_sets]
         hb.loc.copy_(torch.from_numpy(src["loc"])); hb.conf.copy_(torch.from_numpy(src["conf"]))
-        hb.targets = [torch.from_numpy(t) for t in src["targets"]]
+        hb.targets = [torch.from_numpy(t) for t in src["targets"]] if do_loss else None
         hb.ticket = None
         hbufs.append(hb)
 
@@ -350,7 +546,7 @@ def run_ours(a):
         hb = hbufs[i % n_host]
         if hb.ticket is not None:
             pipe.wait(hb.ticket)                                 # this buffer set's previous results are on the host
-        hb.ticket = pipe.submit(hb, hb.targets)
+        hb.ticket = pipe.submit(hb, hb.targets, detect=do_det)
 
     def drain():
         for hb in hbufs:
@@ -358,12 +554,20 @@ def run_ours(a):
                 pipe.wait(hb.ticket)
                 hb.ticket = None
 
-    h2d = B * P * (16 + 8) + sum(t.numel() * 4 for t in hbufs[0].targets) + 4 * (B + 1)
-    d2h = 8 + B * 2 * TOP_K * 5 * 4
-    e2e_steps = max(10, min(a.steps, 500))
+    h2d = B * P * (16 + 8) + ((sum(t.numel() * 4 for t in hbufs[0].targets) + 4 * (B + 1)) if do_loss else 0)
+    d2h = (8 if do_loss else 0) + (B * 2 * TOP_K * 5 * 4 if do_det else 0)
     for i in range(2 * n_host):
         step_e2e(i)
     drain()
+    barrier()
+    K2 = max(10, min(K, 500))
+    t0 = time.perf_counter()
+    for i in range(K2):
+        step_e2e(i)
+    drain()
+    torch.cuda.synchronize()
+    round_s = agree_max(time.perf_counter() - t0)
+    e2e_steps = int(max(1, min(2000, math.ceil(a.min_seconds / max(round_s, 1e-6))))) * K2
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
@@ -382,8 +586,10 @@ def run_ours(a):
     step_e2e(0); drain()
     ll0, lc0, out0 = step_device(dsets[0])
     torch.cuda.synchronize()
-    assert abs(float(hbufs[0].losses[0]) - float(ll0.detach())) <= 1e-6 * abs(float(ll0.detach())) + 1e-7, "e2e loss differs from the device-resident step"
-    assert torch.equal(hbufs[0].detections, out0.cpu()), "e2e Detect output differs from the device-resident step"
+    if do_loss:
+        assert abs(float(hbufs[0].losses[0]) - float(ll0.detach())) <= 1e-6 * abs(float(ll0.detach())) + 1e-7, "e2e loss differs from the device-resident step"
+    if do_det:
+        assert torch.equal(hbufs[0].detections, out0.cpu()), "e2e Detect output differs from the device-resident step"
     clocks = sampler.stop() if sampler else None
     dbg('e2e done')
 
@@ -412,36 +618,40 @@ def run_ours(a):
                 "algorithmic_bytes_per_launch": dom["bytes"], "avg_launch_us": dom["us"],
                 "kernels": [{k: v for k, v in kk.items()} for kk in kern]}
         line = {
-            "metric": METRIC, "value": world * B * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
-            "warmup": max(3, a.warmup), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": world * B * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": max(3, a.warmup), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": a.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "batch_per_gpu": B, "global_batch": world * B, "num_priors": P,
-                       "num_classes": 2, "parallelism": "dp%d (batch-sharded; the 16-byte loss statistics cross ranks as NVLink peer stores from the match kernel)" % world if world > 1 else "dp1",
-                       "l2_policy": "ring of %d distinct input sets (%.0f MB) > L2 (126 MB)" % (n_sets, n_sets * per_set / 1e6),
-                       "launch": ("cuda-graph replay of the public API calls" if graphs is not None else "eager public API calls") + "; Detect on a second stream beside the loss",
-                       "kernels_per_step": kernels_per_step,
-                       "targets": "value: packed ground truth resident in HBM; e2e: host list of [n_i,5] tensors packed and copied every step",
-                       "detect_scores": "softmax(conf + (0,-4)) evaluated inside the Detect kernel (the CPU arm reads the same scores precomputed)"},
+            "config": config_dict(a, P),
+            "details": {"steps_arg": K, "rounds_of_steps_arg": rounds,
+                        "exchange": "batch-sharded; the 16-byte loss statistics cross ranks as NVLink peer stores issued by the kernels" if world > 1 else "none (1 rank)",
+                        "l2_ring": "%d distinct input sets (%.0f MB)" % (n_sets, n_sets * per_set / 1e6),
+                        "launch": ("cuda-graph replay of the public API calls" if graphs is not None else "eager public API calls") + ("; Detect on a second stream beside the loss" if a.mode == "both" else ""),
+                        "kernels_per_step": kernels_per_step, "host_numa": numa,
+                        "targets": "value: packed ground truth resident in HBM; e2e: host list of [n_i,5] tensors packed and copied every step",
+                        "detect_scores": "softmax(conf + (0,-4)) evaluated inside the Detect kernel (the CPU arm reads the same scores precomputed)"},
             "clocks": clocks,
             "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "h2d_gbs_per_rank": h2d * e2e_steps / (e2e_ms * 1e-3) / 1e9,
                     "pipeline": "native host-buffer call (gssd_pipe_submit), 3 steps in flight: H2D beside the previous step's kernels and D2H",
                     "serial_ms_per_step": e2e_serial_ms},
             "gpu_launches": int(gpu_launches),
             "roofline": roof,
         }
+        if parity is not None:
+            line["parity_check"] = parity
         if not a.no_cpu_baseline and world == 1:                 # the CPU arm is timed on rank 0 at N = 1 only
-            from oracle import oracle as O
             priors_np = priors.cpu().numpy()
+            threads = cpu_threads()
             done, dt = time_cpu(a, priors_np, host, 10 ** 9, 1, a.cpu_seconds)
-            line["cpu_baseline"] = {"value": done * B / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": "%d steps of the batch-%d workload in %.1f s (oracle/gssd_oracle.c, OpenMP over images)" % (done, B, dt)}
-        if not a.no_gconv and world == 1:
+            line["cpu_baseline"] = {"value": done * B / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": cpu_sample_text(a, done, dt)}
+        if not a.no_gconv and world == 1 and a.config == 1:
             try:
                 line["gconv"] = time_gconv(a, torch, dev, B)
             except Exception as e:                               # pragma: no cover
                 line["gconv"] = {"error": repr(e)}
-        if (a.sweep or world == 1) and not a.no_sweep:
+        if (a.sweep or (world == 1 and a.config == 1)) and not a.no_sweep:
             line["roofline_sweep"] = sweep(a, lib, _lib, torch, dev, pack_targets)
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -498,9 +708,13 @@ def time_kernels(a, lib, _lib, torch, dev, priors, dsets, pack_targets, B, P, it
                                           TOP_K, CONF_THRESH, NMS_THRESH, 0.1, 0.2, out.data_ptr(), None, None, st))
 
     res = []
-    specs = [("gssd_mbox_match (match_kernel: IoU sweep + conf max)", k_match, B * P * (16 + 8 + 2)),
-             ("gssd_mbox_loss (loss_kernel: encode + smooth-L1 + OHNM select + CE + grads)", k_loss, B * P * 64),
-             ("gssd_detect_logits (detect_kernel: softmax + threshold + top-k + decode + NMS)", k_det, B * (P * 40 + 8000))]
+    mode = getattr(a, "mode", "both")
+    specs = []
+    if mode in ("both", "loss"):
+        specs += [("gssd_mbox_match (match_kernel: IoU sweep + conf max)", k_match, B * P * (16 + 8 + 2)),
+                  ("gssd_mbox_loss (loss_kernel: encode + smooth-L1 + OHNM select + CE + grads)", k_loss, B * P * 64)]
+    if mode in ("both", "detect"):
+        specs += [("gssd_detect_logits (detect_kernel: softmax + threshold + top-k + decode + NMS)", k_det, B * (P * 40 + 8000))]
     k_match(0)
     for name, fn, nbytes in specs:
         for i in range(3):
@@ -588,7 +802,7 @@ def sweep(a, lib, _lib, torch, dev, pack_targets):
             dsets.append(dict(loc=torch.randn((B, P, 4), device=dev) * 0.5, conf=conf,
                               scores=torch.softmax(conf + torch.tensor([0.0, -4.0], device=dev), -1),
                               targets=[torch.from_numpy(t).to(dev) for t in syn.targets(r, B, 1, gmax)]))
-        for k in time_kernels(a, lib, _lib, torch, dev, pri, dsets, pack_targets, B, P, iters=12):
+        for k in time_kernels(argparse.Namespace(mode="both"), lib, _lib, torch, dev, pri, dsets, pack_targets, B, P, iters=12):
             rows.append({"priors": pname, "batch": B, "gmax": gmax, "kernel": k["name"].split(" ")[0], "us": k["us"],
                          "gbs": k["gbs"], "frac": k["gbs"] / hbm})
         del dsets

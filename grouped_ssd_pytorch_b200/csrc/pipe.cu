@@ -12,7 +12,7 @@ struct gssd_pipe {
     gssd_pipe_slot slot[8];
     cudaStream_t s_copy, s_main, s_side;
     cudaEvent_t ev_in[8], ev_free[8], ev_side[8], ev_done[8];
-    bool busy[8], begun[8];
+    bool busy[8], begun[8], loss_on[8];
     int g_sum[8], g_max[8];
     int64_t next;
     bool use_x;
@@ -57,14 +57,20 @@ int64_t cuda_err(cudaError_t e) { return -(1000 + (int64_t)e); }
 int64_t begin_step(gssd_pipe *p, const float *loc_h, const float *conf_h, const float *scores_h, const float *gt_h,
                    const int32_t *gt_off_h, int sum_g, int g_max, float *det_h) {
     const gssd_pipe_cfg &c = p->cfg;
-    if (!loc_h || !conf_h || !gt_h || !gt_off_h || sum_g <= 0 || g_max <= 0) return GSSD_ERR_ARG;
-    if (sum_g > c.max_gt_rows) return GSSD_ERR_LIMIT;
-    // the row offsets are host memory: check them here, the kernels size their shared memory from g_max and index gt by them
-    if (gt_off_h[0] != 0 || gt_off_h[c.B] != sum_g) return GSSD_ERR_ARG;
-    for (int b = 0; b < c.B; ++b) {
-        const int rows = gt_off_h[b + 1] - gt_off_h[b];
-        if (rows <= 0) return rows == 0 ? GSSD_ERR_EMPTY : GSSD_ERR_ARG;
-        if (rows > g_max) return GSSD_ERR_ARG;
+    // gt_h == NULL: a Detect-only step (inference, ssd_multiphase_custom_group.py:384-390) — no matching, no loss
+    const bool do_loss = gt_h != nullptr;
+    if (!loc_h || !conf_h) return GSSD_ERR_ARG;
+    if (!do_loss && !det_h) return GSSD_ERR_ARG;
+    if (do_loss) {
+        if (!gt_off_h || sum_g <= 0 || g_max <= 0) return GSSD_ERR_ARG;
+        if (sum_g > c.max_gt_rows) return GSSD_ERR_LIMIT;
+        // the row offsets are host memory: check them here, the kernels size their shared memory from g_max and index gt by them
+        if (gt_off_h[0] != 0 || gt_off_h[c.B] != sum_g) return GSSD_ERR_ARG;
+        for (int b = 0; b < c.B; ++b) {
+            const int rows = gt_off_h[b + 1] - gt_off_h[b];
+            if (rows <= 0) return rows == 0 ? GSSD_ERR_EMPTY : GSSD_ERR_ARG;
+            if (rows > g_max) return GSSD_ERR_ARG;
+        }
     }
     const int64_t ticket = p->next;
     const int k = (int)(ticket % c.depth);
@@ -87,11 +93,14 @@ int64_t begin_step(gssd_pipe *p, const float *loc_h, const float *conf_h, const 
         PIPE_CUDA(cudaMemcpyAsync(s.conf, conf_h, n_conf, cudaMemcpyHostToDevice, p->s_copy));
         if (have_scores) PIPE_CUDA(cudaMemcpyAsync(s.scores, scores_h, n_conf, cudaMemcpyHostToDevice, p->s_copy));
     }
-    PIPE_CUDA(cudaMemcpyAsync(s.gt, gt_h, (size_t)sum_g * 5 * 4, cudaMemcpyHostToDevice, p->s_copy));
-    PIPE_CUDA(cudaMemcpyAsync(s.gt_off, gt_off_h, (size_t)(c.B + 1) * 4, cudaMemcpyHostToDevice, p->s_copy));
+    if (do_loss) {
+        PIPE_CUDA(cudaMemcpyAsync(s.gt, gt_h, (size_t)sum_g * 5 * 4, cudaMemcpyHostToDevice, p->s_copy));
+        PIPE_CUDA(cudaMemcpyAsync(s.gt_off, gt_off_h, (size_t)(c.B + 1) * 4, cudaMemcpyHostToDevice, p->s_copy));
+    }
     PIPE_CUDA(cudaEventRecord(p->ev_in[k], p->s_copy));
     PIPE_CUDA(cudaStreamWaitEvent(p->s_main, p->ev_in[k], 0));
-    if (p->use_x)
+    if (!do_loss) {
+    } else if (p->use_x)
         PIPE_RC(gssd_mbox_match_x(p->priors, c.P, s.conf, c.C, s.gt, s.gt_off, c.B, sum_g, g_max, c.match_thresh, s.tags, s.stats, &p->x, p->s_main));
     else
         PIPE_RC(gssd_mbox_match(p->priors, c.P, s.conf, c.C, s.gt, s.gt_off, c.B, sum_g, g_max, c.match_thresh, s.tags, s.stats, p->s_main));
@@ -106,18 +115,20 @@ int64_t begin_step(gssd_pipe *p, const float *loc_h, const float *conf_h, const 
         PIPE_CUDA(cudaMemcpyAsync(det_h, s.detect_out, (size_t)c.B * c.C * c.top_k * 5 * 4, cudaMemcpyDeviceToHost, p->s_side));
     }
     PIPE_CUDA(cudaEventRecord(p->ev_side[k], p->s_side));
-    p->g_sum[k] = sum_g; p->g_max[k] = g_max; p->begun[k] = true;
+    p->g_sum[k] = sum_g; p->g_max[k] = g_max; p->begun[k] = true; p->loss_on[k] = do_loss;
     p->next = ticket + 1;
     return ticket;
 }
 
 int64_t finish_step(gssd_pipe *p, int64_t ticket, const gssd_loss_stats *global_stats, int n_global, float *losses_h) {
     const gssd_pipe_cfg &c = p->cfg;
-    if (ticket < 0 || ticket >= p->next || ticket + c.depth < p->next || !losses_h) return GSSD_ERR_ARG;
+    if (ticket < 0 || ticket >= p->next || ticket + c.depth < p->next) return GSSD_ERR_ARG;
     const int k = (int)(ticket % c.depth);
     if (!p->begun[k]) return GSSD_ERR_ARG;
+    if (p->loss_on[k] && !losses_h) return GSSD_ERR_ARG;
     const gssd_pipe_slot &s = p->slot[k];
-    if (p->use_x && global_stats == nullptr)
+    if (!p->loss_on[k]) {
+    } else if (p->use_x && global_stats == nullptr)
         PIPE_RC(gssd_mbox_loss_x(s.loc, s.conf, p->priors, c.B, c.P, c.C, s.gt, s.gt_off, p->g_sum[k], p->g_max[k], s.tags, s.stats,
                                  &p->x, c.negpos_ratio, c.var0, c.var1, s.losses, s.grad_loc, s.grad_conf, nullptr, nullptr,
                                  s.ws, s.ws_bytes, p->s_main));
@@ -125,7 +136,7 @@ int64_t finish_step(gssd_pipe *p, int64_t ticket, const gssd_loss_stats *global_
         PIPE_RC(gssd_mbox_loss(s.loc, s.conf, p->priors, c.B, c.P, c.C, s.gt, s.gt_off, p->g_sum[k], p->g_max[k], s.tags, s.stats,
                                global_stats, n_global, c.negpos_ratio, c.var0, c.var1, s.losses, s.grad_loc, s.grad_conf, nullptr, nullptr,
                                s.ws, s.ws_bytes, p->s_main));
-    PIPE_CUDA(cudaMemcpyAsync(losses_h, s.losses, 8, cudaMemcpyDeviceToHost, p->s_main));
+    if (p->loss_on[k]) PIPE_CUDA(cudaMemcpyAsync(losses_h, s.losses, 8, cudaMemcpyDeviceToHost, p->s_main));
     PIPE_CUDA(cudaStreamWaitEvent(p->s_main, p->ev_side[k], 0));             // Detect and its D2H belong to the step
     PIPE_CUDA(cudaEventRecord(p->ev_free[k], p->s_main));
     PIPE_CUDA(cudaEventRecord(p->ev_done[k], p->s_main));
@@ -157,7 +168,7 @@ extern "C" int gssd_pipe_create(gssd_pipe **out, const gssd_pipe_cfg *cfg, const
     cudaError_t e = cudaSuccess;
     for (int k = 0; k < cfg->depth; ++k) {
         layout_slot(*cfg, base + per * k, &p->slot[k]);
-        p->busy[k] = p->begun[k] = false;
+        p->busy[k] = p->begun[k] = p->loss_on[k] = false;
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_main, cudaStreamNonBlocking);

@@ -89,6 +89,14 @@ class Detect(object):
                            cfg['variance'], logits=True, class_bias=class_bias)
 
     @staticmethod
+    def apply_logits_with_indices(num_classes, bkg_label, top_k, conf_thresh, nms_thresh, loc_data, conf_logits, prior_data,
+                                  class_bias=None):
+        """`apply_logits` + (count[B,C], keep_idx[B,C,top_k]) as `apply_with_indices`."""
+        with torch.no_grad():
+            return _detect(num_classes, top_k, conf_thresh, nms_thresh, loc_data, conf_logits, prior_data,
+                           cfg['variance'], want_aux=True, logits=True, class_bias=class_bias)
+
+    @staticmethod
     def apply_with_indices(num_classes, bkg_label, top_k, conf_thresh, nms_thresh, loc_data, conf_data, prior_data):
         """-> (output, count[B,C] int32, keep_idx[B,C,top_k] int32 prior indices, -1 padded)."""
         with torch.no_grad():

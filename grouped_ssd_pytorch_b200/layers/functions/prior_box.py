@@ -1,4 +1,9 @@
 """PriorBox — same constructor/forward as layers/functions/prior_box.py:5-172 of the reference."""
+import hashlib
+import json
+import os
+
+import numpy as np
 import torch
 
 from ... import _lib
@@ -27,8 +32,21 @@ class PriorBox(object):
                 raise ValueError('Variances must be greater than 0')
         self._cfg = dict(cfg)
 
+    def _cache_file(self):
+        """GSSD_PRIOR_CACHE=<dir>: the boxes the kernel produced are serialised there (one .npy per configuration), so that a
+        model object — the reference builds its priors inside SSD.__init__, ssd_multiphase_custom_group.py:48-49 — can be
+        CONSTRUCTED on a box without a GPU (checkpoint surgery, the CPU import tests).  Nothing is computed on the CPU."""
+        d = os.environ.get("GSSD_PRIOR_CACHE")
+        if not d:
+            return None
+        key = json.dumps({k: self._cfg[k] for k in sorted(self._cfg)}, sort_keys=True, default=str)
+        return os.path.join(d, "priors_%s_%s.npy" % (self.version, hashlib.sha1(key.encode()).hexdigest()[:16]))
+
     def forward(self, device=None):
         """-> FloatTensor[P,4] on the CPU like the reference (prior_box.py:168), or on `device`."""
+        cache = self._cache_file()
+        if not torch.cuda.is_available() and cache is not None and os.path.exists(cache):
+            return torch.from_numpy(np.load(cache))
         lib = _lib.require_cuda()
         c = _lib.prior_cfg(self._cfg)
         n = lib.gssd_priorbox_count(c)
@@ -37,4 +55,7 @@ class PriorBox(object):
         with torch.cuda.device(dev):
             out = torch.empty((n, 4), dtype=torch.float32, device=dev)
             _lib.check(lib.gssd_priorbox(c, out.data_ptr(), _lib.stream()), "gssd_priorbox")
+        if cache is not None and not os.path.exists(cache):
+            os.makedirs(os.path.dirname(cache), exist_ok=True)
+            np.save(cache, out.cpu().numpy())
         return out if device is not None and torch.device(device).type == "cuda" else out.cpu()

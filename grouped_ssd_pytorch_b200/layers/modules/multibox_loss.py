@@ -71,20 +71,31 @@ class _MultiBoxLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_l, g_c, *_unused):
+        """d(loss_l)/d(loc) and d(loss_c)/d(conf) were produced by the forward kernel; they are scaled by the upstream gradients.
+        `(loss_l + loss_c).backward()` (train_lesion_multiphase_v2.py:247-248; both upstream gradients present) scales the
+        buffers in place — a kernel that returns at once when both are 1 — and hands them to autograd without a copy.  When only
+        one of the two losses is being differentiated (`loss_l.backward(retain_graph=True); loss_c.backward()`,
+        `torch.autograd.grad(loss_c, conf)`) the buffers are kept intact and a scaled copy of the one that takes part is returned,
+        so that the other loss can still be differentiated afterwards."""
+        if ctx.grads is None:
+            raise RuntimeError("MultiBoxLoss: the gradient buffers of this forward were already handed to autograd by a backward "
+                               "through both losses; differentiate loss_l and loss_c separately, or call forward again")
         grad_loc, grad_conf = ctx.grads
-        ctx.grads = None                       # hand the buffers over: autograd can adopt them without a copy
         if grad_loc is None:
             return (None,) * 12
         lib = _lib.load()
-        with torch.cuda.device(grad_loc.device):
-            if g_l is None:                    # that loss took no part in what was differentiated
-                g_l = torch.zeros((), dtype=torch.float32, device=grad_loc.device)
-            if g_c is None:
-                g_c = torch.zeros((), dtype=torch.float32, device=grad_loc.device)
-            if not (g_l.is_cuda and g_l.dtype == torch.float32):
-                g_l = g_l.to(device=grad_loc.device, dtype=torch.float32)
-            if not (g_c.is_cuda and g_c.dtype == torch.float32):
-                g_c = g_c.to(device=grad_loc.device, dtype=torch.float32)
+        dev = grad_loc.device
+
+        def scalar(g):
+            return g if (g.is_cuda and g.dtype == torch.float32) else g.to(device=dev, dtype=torch.float32)
+
+        with torch.cuda.device(dev):
+            if g_l is None or g_c is None:     # one loss only: out of place, the buffers stay valid for the other one
+                out_l = grad_loc * scalar(g_l) if g_l is not None else None
+                out_c = grad_conf * scalar(g_c) if g_c is not None else None
+                return (out_l, out_c) + (None,) * 10
+            ctx.grads = None                   # hand the buffers over: autograd can adopt them without a copy
+            g_l, g_c = scalar(g_l), scalar(g_c)
             _lib.check(lib.gssd_mbox_scale_grads(grad_loc.data_ptr(), grad_loc.numel(), grad_conf.data_ptr(),
                                                  grad_conf.numel(), g_l.data_ptr(), g_c.data_ptr(), _lib.stream()),
                        "gssd_mbox_scale_grads")

@@ -95,9 +95,19 @@ class HostPipeline(object):
         return base, base + sum_g * 5 * 4, sum_g, g_max
 
     def submit(self, bufs, targets, detect=True):
-        """enqueue one step on `bufs` (its loc/conf/scores are read, its losses/detections written); returns the ticket"""
-        gt_p, off_p, sum_g, g_max = self._pack(bufs, targets)
+        """enqueue one step on `bufs` (its loc/conf/scores are read, its losses/detections written); returns the ticket.
+        targets=None: a Detect-only step (inference) — no matching, no loss."""
         lib, h = self._lib, self._h
+        if targets is None:
+            if not detect:
+                raise ValueError("HostPipeline.submit: nothing to do (no targets and detect=False)")
+            sc = bufs.scores.data_ptr() if bufs.scores is not None else None
+            t = lib.gssd_pipe_submit(h, bufs.loc.data_ptr(), bufs.conf.data_ptr(), sc, None, None, 0, 0, None,
+                                     bufs.detections.data_ptr())
+            if t < 0:
+                self._raise(t, "gssd_pipe_submit")
+            return t
+        gt_p, off_p, sum_g, g_max = self._pack(bufs, targets)
         sc = bufs.scores.data_ptr() if (detect and bufs.scores is not None) else None
         det = bufs.detections.data_ptr() if detect else None
         _, world, _ = gdist.world(self.group)

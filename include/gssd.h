@@ -332,7 +332,9 @@ GSSD_API int     gssd_pipe_slot_info(const gssd_pipe *p, int slot, gssd_pipe_slo
  * gt_off_host[B+1] are the packed ground truth.  losses_host[2], detect_out_host[B,C,top_k,5].
  * The row offsets are checked on the host before anything is enqueued: gt_off_host[0] == 0, gt_off_host[B] == sum_g, every
  * image has between 1 and g_max rows (GSSD_ERR_EMPTY for an image without ground truth — the reference raises IndexError,
- * box_utils.py:94 — GSSD_ERR_ARG otherwise); GSSD_ERR_ARG too when the slot's previous gssd_pipe_begin was never finished. */
+ * box_utils.py:94 — GSSD_ERR_ARG otherwise); GSSD_ERR_ARG too when the slot's previous gssd_pipe_begin was never finished.
+ * gt_host == NULL makes it a Detect-only step (inference: H2D of loc / conf, Detect, D2H of the detections; no matching, no
+ * loss, losses_host may be NULL); detect_out_host == NULL a loss-only step. */
 GSSD_API int64_t gssd_pipe_submit(gssd_pipe *p, const float *loc_host, const float *conf_host, const float *scores_host,
                          const float *gt_host, const int32_t *gt_off_host, int sum_g, int g_max,
                          float *losses_host, float *detect_out_host);

@@ -73,6 +73,16 @@ def lib():
     return _lib
 
 
+def set_threads(n):
+    """OpenMP threads the oracle's image loops use from now on (torchrun exports OMP_NUM_THREADS=1, which would
+    otherwise silently make the CPU arm single-threaded); returns the count in effect."""
+    lib()
+    omp = C.CDLL("libgomp.so.1")                      # the instance the oracle library is linked against
+    if n and n > 0:
+        omp.omp_set_num_threads(int(n))
+    return int(omp.omp_get_max_threads())
+
+
 def _f(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 

@@ -159,6 +159,68 @@ def test_install_as_layers_resolves_reference_imports():
                 sys.modules[k] = v
 
 
+REF = "/root/reference/ssd_liverdet"
+
+_DROPIN_SCRIPT = r"""
+import os, sys, types
+import numpy as np
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(ref)r)
+dcn = types.ModuleType("dcn_v2"); dcn._DCNv2 = type("_DCNv2", (), {"apply": staticmethod(lambda *a: None)}); sys.modules["dcn_v2"] = dcn
+mpl = types.ModuleType("matplotlib"); mpl.use = lambda *a, **k: None
+sys.modules["matplotlib"] = mpl; sys.modules["matplotlib.pyplot"] = types.ModuleType("matplotlib.pyplot")
+if %(preimport)r:
+    import layers                                   # the reference's own package is already imported: install must replace it
+    assert "grouped_ssd" not in layers.MultiBoxLoss.__module__
+import grouped_ssd_pytorch_b200 as gssd
+gssd.install_as_layers()
+# the serialised priors of the v2 configuration (the kernel's output, bit-identical to the reference's: test_gpu_parity)
+from grouped_ssd_pytorch_b200 import config
+from grouped_ssd_pytorch_b200.layers import PriorBox
+os.environ["GSSD_PRIOR_CACHE"] = %(cache)r
+os.makedirs(%(cache)r, exist_ok=True)
+np.save(PriorBox(config.v2)._cache_file(), np.load(os.path.join(%(root)r, "tests", "golden", "priors.npz"))["v2"])
+# the imports of models/ssd_multiphase_custom_group.py:5-10 and train_lesion_multiphase_v2.py:14,17
+from layers import *
+from layers import self_attn
+from layers.dcn_v2_custom import DCN
+from layers.modules import MultiBoxLoss
+from layers.box_utils import match, log_sum_exp, decode, nms
+from data import DataSplitter, FISHdetectionV2, detection_collate_v2, BaseTransform, v2
+import layers, data
+ours = "grouped_ssd_pytorch_b200"
+assert MultiBoxLoss.__module__.startswith(ours) and Detect.__module__.startswith(ours) and PriorBox.__module__.startswith(ours)
+assert L2Norm.__module__.startswith(ours) and match.__module__.startswith(ours)
+assert self_attn.__file__.startswith(%(ref)r) and DCN.__module__ == "layers.dcn_v2_custom"
+assert data.__file__.startswith(%(ref)r), "the reference's data package must stay the one that is imported"
+from models.ssd_multiphase_custom_group import build_ssd
+import torch
+net = build_ssd('train', 300, 2, True, 4, 4, 1, True, False, False, 0, 1, False, False, 1)          # GSSD
+assert type(net.L2Norm).__module__.startswith(ours) and type(net.priorbox).__module__.startswith(ours)
+assert tuple(net.priors.shape) == (8732, 4) and sum(p.numel() for p in net.parameters()) == 8340084
+tst = build_ssd('test', 300, 2, True, 4, 4, 1, True, False, False, 0, 1, False, False, 1)
+assert type(tst.detect).__module__.startswith(ours)
+pp = build_ssd('train', 300, 2, True, 4, 4, 1, True, True, True, 1, 4, True, False, 1)               # GSSD++ (SA + DCN)
+assert sum(p.numel() for p in pp.parameters()) == 18488172
+crit = MultiBoxLoss(2, 0.5, True, 0, True, 3, 0.5, False, True)                                      # train_lesion_multiphase_v2.py:639
+print("DROPIN-OK")
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference tree (build container)")
+@pytest.mark.parametrize("preimport", [False, True])
+def test_install_as_layers_builds_the_reference_model(tmp_path, preimport):
+    """INTEGRATION.md option A with the reference's OWN code: after install_as_layers() the model file of the reference
+    (models/ssd_multiphase_custom_group.py) imports, its `from layers import *` / `from layers import self_attn` /
+    `from layers.dcn_v2_custom import DCN` / `from data import v2` resolve, and build_ssd constructs GSSD and GSSD++ with our
+    PriorBox / L2Norm / Detect inside (no GPU here: the priors come from the serialised cache, nothing runs)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = _DROPIN_SCRIPT % dict(root=root, ref=REF, cache=str(tmp_path / "priors"), preimport=preimport)
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "DROPIN-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def test_reference_visible_errors_without_gpu_work():
     from grouped_ssd_pytorch_b200.layers import Detect, PriorBox
     bad = dict(config.v2); bad["variance"] = [0.0, 0.2]

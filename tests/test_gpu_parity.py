@@ -226,16 +226,19 @@ def test_multibox_loss_vs_oracle(B, gmax, pname, C):
     assert check_loss_against_oracle(loc, conf, pri, tg, C, 3, res) >= max(1, B // 2)
 
 
-def test_multibox_loss_key_ties_at_cut():
+@pytest.mark.parametrize("pname,step", [("small", 0.25), ("v2", 0.002), ("v2_512", 0.001)])
+def test_multibox_loss_key_ties_at_cut(pname, step):
     """exact duplicate keys straddling the num_neg cut: lower prior index first (the oracle's stable
-    rule); plus saturated rows whose key underflows to 0 and ties with the zeroed positives."""
-    pri = cases.priors("small")
+    rule); plus saturated rows whose key underflows to 0 and ties with the zeroed positives.
+    "small": one CTA per image; "v2" / "v2_512": a batch of 3 runs 8 CTAs per image, so that "more than 32 keys exactly
+    equal at the cut" (image 2: every key identical; image 1: every second key 0) goes through the cluster code."""
+    pri = cases.priors(pname)
     P = pri.shape[0]
     r = syn.rng(77)
     tg = syn.targets(r, 3, 2, 3)
     loc = syn.loc(r, 3, P)
     conf = np.zeros((3, P, 2), np.float32)
-    conf[0, :, 1] = np.repeat(np.arange(P // 8 + 1), 8)[:P] * 0.25      # blocks of 8 equal keys
+    conf[0, :, 1] = np.repeat(np.arange(P // 8 + 1), 8)[:P] * step      # blocks of 8 equal keys
     conf[1] = syn.conf_logits(r, 1, P, 2)[0]
     conf[1, ::2] = np.array([40.0, -40.0], np.float32)                   # key == 0 exactly
     conf[2, :, 1] = 1.0                                                  # every key identical
@@ -268,6 +271,34 @@ def test_multibox_loss_api_variants():
     assert c.grad is None or not c.grad.any()
     with pytest.raises(IndexError):
         crit((cu(loc), cu(conf), cu(pri)), [cu(tg[0]), torch.zeros(0, 5).cuda(), cu(tg[2]), cu(tg[3])])
+
+
+def test_multibox_loss_separate_and_retained_backward():
+    """`loss_l.backward(retain_graph=True); loss_c.backward()` and torch.autograd.grad on each loss separately give the
+    oracle's gradients (the advisor's round-1 finding: the second call used to return None silently)."""
+    loc, conf, pri, tg, C, ratio = cases.loss_case("a")
+    o = O.multibox_loss(loc, conf, pri, tg, 0.5, ratio, cases.VAR)
+    crit = MultiBoxLoss(C, 0.5, True, 0, True, ratio, 0.5, False, True)
+    l = cu(loc).requires_grad_(); c = cu(conf).requires_grad_()
+    ll, lc = crit((l, c, cu(pri)), [cu(t) for t in tg])
+    ll.backward(retain_graph=True)
+    close(l.grad, o["grad_loc"], atol=1e-9)
+    assert c.grad is None or not c.grad.any()
+    lc.backward()
+    close(l.grad, o["grad_loc"], atol=1e-9)
+    close(c.grad, o["grad_conf"], atol=1e-9)
+    # torch.autograd.grad, one loss at a time, conf first, with non-unit upstream gradients
+    l = cu(loc).requires_grad_(); c = cu(conf).requires_grad_()
+    ll, lc = crit((l, c, cu(pri)), [cu(t) for t in tg])
+    (gc,) = torch.autograd.grad(lc, c, grad_outputs=torch.tensor(3.0, device="cuda"), retain_graph=True)
+    (gl,) = torch.autograd.grad(ll, l, grad_outputs=torch.tensor(0.5, device="cuda"), retain_graph=True)
+    close(gc, 3.0 * o["grad_conf"], rtol=1e-5, atol=1e-9)
+    close(gl, 0.5 * o["grad_loc"], rtol=1e-5, atol=1e-9)
+    # then both at once: in place, buffers handed over; one more backward through both must fail loudly, not return None
+    (ll + lc).backward(retain_graph=True)
+    close(l.grad, o["grad_loc"], atol=1e-9); close(c.grad, o["grad_conf"], atol=1e-9)
+    with pytest.raises(RuntimeError, match="already handed"):
+        (ll + lc).backward()
 
 
 def test_multibox_loss_deterministic():
@@ -365,7 +396,7 @@ def test_detect_vs_oracle(B, pname, C, shift, sigma, thr, top_k):
     out, count, keep = Detect.apply_with_indices(C, 0, top_k, thr, 0.45, cu(loc), cu(conf), cu(pri))
     o = O.detect(loc, conf, pri, C, top_k, thr, 0.45, cases.VAR)
     out, count, keep = out.cpu().numpy(), count.cpu().numpy(), keep.cpu().numpy()
-    n_exact = 0
+    n_exact, skipped = 0, []
     for b in range(B):
         for cl in range(C):
             if o["margin"][b, cl] > 1e-5:      # decoded boxes differ by an ulp (expf): skip knife-edge IoUs
@@ -373,7 +404,12 @@ def test_detect_vs_oracle(B, pname, C, shift, sigma, thr, top_k):
                 eq(out[b, cl, :, 0], o["out"][b, cl, :, 0])
                 close(out[b, cl, :, 1:], o["out"][b, cl, :, 1:])
                 n_exact += 1
-    assert n_exact >= B * C * 0.7
+            else:
+                skipped.append((b, cl, float(o["margin"][b, cl])))
+    print("test_detect_vs_oracle[B=%d %s C=%d]: %d of %d (image, class) slabs compared exactly, %d skipped for an IoU within "
+          "1e-5 of the NMS threshold %s" % (B, pname, C, n_exact, B * C, len(skipped), skipped[:4]))
+    # a skipped slab needs one of its <= 20 k candidate pairs within 1e-5 of the threshold: a handful per thousand slabs
+    assert len(skipped) <= max(1, B * C // 50)
 
 
 def test_detect_equal_scores():
@@ -430,6 +466,43 @@ def test_detect_from_logits_equals_detect_of_softmax(C, bias):
     assert int((want[..., 0] > 0).sum()) > 50
     assert torch.equal(got[..., 1:], want[..., 1:]), "kept boxes differ"
     assert float((got[..., 0] - want[..., 0]).abs().max()) <= 1.2e-7, "scores differ by more than an ulp"
+
+
+@pytest.mark.parametrize("C,bias,B", [(2, None, 3), (2, (0.0, -4.0), 32), (3, (0.5, -2.0, -3.0), 2)])
+def test_detect_from_logits_vs_oracle(C, bias, B):
+    """gssd_detect_logits against the ORACLE (not against our own Detect): the oracle's Detect (detection_pytorch_ver_1point5.py:
+    33-89) is fed softmax(conf + bias) computed by numpy in torch's formula (row max, exp, sum, divide —
+    ssd_multiphase_custom_group.py:388).  numpy's expf and CUDA's can differ in the last ulp, so scores are compared to
+    1.2e-7 and a slab is compared exactly only when no discrete decision sits on such an ulp: score gaps between neighbours in
+    the candidate order, the gap to conf_thresh, the top_k cut and the NMS IoU margin."""
+    from grouped_ssd_pytorch_b200.layers import Detect
+    pri = cases.priors("v2")
+    P = pri.shape[0]
+    r = syn.rng(191 + C)
+    loc = syn.loc(r, B, P, 0.2)
+    logits = syn.conf_logits(r, B, P, C)
+    shifted = logits if bias is None else logits + np.asarray(bias, np.float32)
+    scores = syn.softmax(shifted.astype(np.float32))
+    thr = 0.2
+    o = O.detect(loc, scores, pri, C, 200, thr, 0.45, cases.VAR)
+    got, count, keep = Detect.apply_logits_with_indices(C, 0, 200, thr, 0.45, cu(loc), cu(logits), cu(pri), class_bias=bias)
+    got, count, keep = got.cpu().numpy(), count.cpu().numpy(), keep.cpu().numpy()
+    n_exact, skipped = 0, 0
+    for b in range(B):
+        for cl in range(1, C):
+            sc = np.sort(scores[b, :, cl][scores[b, :, cl] > thr - 1e-6])
+            knife = (sc.size > 1 and np.diff(sc).min() < 4e-7) or (sc.size and np.abs(sc - thr).min() < 4e-7)
+            if knife or o["margin"][b, cl] <= 1e-5 or o["cut_gap"][b, cl] < 4e-7:
+                skipped += 1
+                continue
+            eq(keep[b, cl], o["keep_idx"][b, cl]); assert count[b, cl] == o["count"][b, cl]
+            assert np.abs(got[b, cl, :, 0] - o["out"][b, cl, :, 0]).max() <= 1.2e-7
+            close(got[b, cl, :, 1:], o["out"][b, cl, :, 1:])
+            n_exact += 1
+        assert not got[b, 0].any()
+    print("test_detect_from_logits_vs_oracle[C=%d B=%d]: %d slabs exact, %d skipped (a decision within an ulp)" % (C, B, n_exact, skipped))
+    assert n_exact >= 1 and skipped <= max(1, B * (C - 1) // 8)
+    assert int(count.sum()) > 50
 
 
 def test_collect_detections_mirrors_the_evaluator_loop():
