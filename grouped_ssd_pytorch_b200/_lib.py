@@ -7,7 +7,7 @@ import torch
 
 from . import build as _build
 
-ERR_ARG, ERR_LIMIT, ERR_WS, ERR_VALUE, ERR_EMPTY = -1, -2, -3, -4, -5
+ERR_ARG, ERR_LIMIT, ERR_WS, ERR_VALUE, ERR_EMPTY, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 MAX_MAPS, MAX_AR = 8, 8
 PRIOR_V2, PRIOR_V2_CUSTOM, PRIOR_LEGACY = 0, 1, 2
 WS_LSE, WS_MATCH, WS_LOSS, WS_NMS = 0, 1, 2, 3
@@ -49,7 +49,7 @@ class PipeCfg(C.Structure):
 class PipeSlot(C.Structure):
     """`gssd_pipe_slot` (include/gssd.h): device addresses as integers."""
     _fields_ = [(n, C.c_void_p) for n in ("loc", "conf", "scores", "gt", "gt_off", "tags", "stats", "losses", "grad_loc",
-                                          "grad_conf", "detect_out", "ws")] + [("ws_bytes", C.c_size_t)]
+                                          "grad_conf", "detect_out", "ws")] + [("ws_bytes", C.c_size_t), ("fused_state", C.c_void_p)]
 
 
 XCHG_MAX_RANKS, XCHG_HANDLE_BYTES = 16, 64
@@ -57,7 +57,8 @@ XCHG_MAX_RANKS, XCHG_HANDLE_BYTES = 16, 64
 
 class Xchg(C.Structure):
     """`gssd_xchg` (include/gssd.h)."""
-    _fields_ = [("peers", C.c_void_p * XCHG_MAX_RANKS), ("rank", C.c_int32), ("world", C.c_int32)]
+    _fields_ = [("peers", C.c_void_p * XCHG_MAX_RANKS), ("rank", C.c_int32), ("world", C.c_int32),
+                ("timeout_ms", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 MAX_GT_PER_IMAGE = 128
@@ -81,6 +82,10 @@ _SIGS = {
     "gssd_mbox_match": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _F, _P, _P, _P]),
     "gssd_mbox_loss": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _I, _I, _F, _F,
                             _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "gssd_fused_state_bytes": (_SZ, []),
+    "gssd_mbox_fused_supported": (_I, [_I, _I, _I, _I]),
+    "gssd_mbox_loss_fused": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _F, _I, _F, _F, _P, C.POINTER(Xchg),
+                                  _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "gssd_mbox_scale_grads": (_I, [_P, _SZ, _P, _SZ, _P, _P, _P]),
     "gssd_detect": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P]),
     "gssd_detect_logits": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P]),
@@ -132,7 +137,7 @@ def load():
     for name, (res, args) in _SIGS.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.gssd_abi_version() != 1:
+    if lib.gssd_abi_version() != 2:
         raise RuntimeError("libgssd_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -176,6 +181,20 @@ def f32(t, dev):
     if not isinstance(t, torch.Tensor):
         t = torch.as_tensor(t)
     return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+_fused_states = {}
+
+
+def fused_state(dev, stream_ptr):
+    """the zero-initialised rendezvous state of the one-launch MultiBoxLoss (include/gssd.h: gssd_mbox_loss_fused), one per
+    (device, stream): launches that share a state must be ordered on one stream, and the kernel leaves it zeroed."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), int(stream_ptr))
+    t = _fused_states.get(key)
+    if t is None:
+        t = torch.zeros((max(64, int(load().gssd_fused_state_bytes())),), dtype=torch.uint8, device=dev)
+        _fused_states[key] = t
+    return t
 
 
 def launch_count():

@@ -20,6 +20,7 @@ extern "C" const char *gssd_error_string(int code) {
         case GSSD_ERR_WS: return "workspace too small (see gssd_workspace_bytes)";
         case GSSD_ERR_VALUE: return "value error (variance <= 0 or nms_thresh <= 0)";
         case GSSD_ERR_EMPTY: return "an image has no ground-truth box";
+        case GSSD_ERR_UNSUPPORTED: return "shape not supported by the one-launch path (use the two stages)";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
     }
 }

@@ -8,6 +8,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/gssd.h"
 
@@ -90,24 +91,31 @@ static inline int resident_ctas(const void *kern, int threads, size_t smem) {
 }
 
 // ---- peer exchange of the loss statistics (gssd_xchg, include/gssd.h) ---------------------------------------
-struct XSlot { uint32_t conf_max_ord; int32_t num_pos; uint32_t epoch; uint32_t pad; };
+// One 64-bit word per (value, step parity, source rank): (epoch << 32) | value.  Value and tag travel in ONE naturally
+// aligned 8-byte store, so a reader that sees the epoch of the current step also sees the value — no fence between them.
 struct XBuf {
-    XSlot slot[2][GSSD_XCHG_MAX_RANKS];     // [step parity][source rank]
-    uint32_t epoch;                          // this rank's step counter (advanced by the last CTA of stage 1)
-    uint32_t match_done;                     // CTA counter of the running stage-1 kernel
+    unsigned long long xmax[2][GSSD_XCHG_MAX_RANKS];   // max of conf (ordered uint32) of every rank
+    unsigned long long npos[2][GSSD_XCHG_MAX_RANKS];   // number of positives of every rank
+    uint32_t epoch;                          // completed steps (advanced by the LAST CTA of a step's last kernel)
+    uint32_t match_done;                     // CTA counter of the running stage-1 kernel (two-launch path)
 };
 struct XDev {                                // kernel-argument image of gssd_xchg
     XBuf *peers[GSSD_XCHG_MAX_RANKS];
     int rank, world;                         // world == 0: exchange disabled
+    unsigned long long timeout_ns;           // a wait for a peer's word that lasts longer traps (0 = wait for ever)
 };
 static inline XDev xdev_from(const gssd_xchg *x) {
     XDev d = {};
     if (x != nullptr) {
         for (int r = 0; r < GSSD_XCHG_MAX_RANKS; ++r) d.peers[r] = reinterpret_cast<XBuf *>(x->peers[r]);
         d.rank = x->rank; d.world = x->world;
+        d.timeout_ns = (unsigned long long)x->timeout_ms * 1000000ull;
     }
     return d;
 }
+
+// rendezvous state of the one-launch MultiBoxLoss (fused.cu): zero-initialised once, reset by the last CTA of every launch
+struct FusedState { uint32_t bar1, bar2, xmax_ord; int32_t n_pos; uint32_t done; uint32_t pad[3]; };
 
 // ---- optional phase timing (debug build only: -DGSSD_PHASE_TIMING, see tools/phase_times.py) ----------
 #ifdef GSSD_PHASE_TIMING

@@ -67,30 +67,32 @@ __global__ void __launch_bounds__(LOSS_NT, 4) loss_kernel(LossArgs a) {
 
     // batch-global scalars: max over ranks of x_max, sum over ranks of N
     float x_max; int n_total;
+    uint32_t x_epoch = 0;
     if (a.x.world > 0) {
         // peer exchange: wait until every rank's stage 1 has stored its statistics of THIS step into our buffer
         __shared__ uint32_t s_mo; __shared__ int s_nt;
+        const XBuf *xl = a.x.peers[a.x.rank];
+        x_epoch = *reinterpret_cast<const volatile uint32_t *>(&xl->epoch) + 1;
         if (warp == 0) {
-            const XBuf *xl = a.x.peers[a.x.rank];
-            const uint32_t e = *reinterpret_cast<const volatile uint32_t *>(&xl->epoch);
             uint32_t mo = 0; int nt = 0;
             if (lane < a.x.world) {
-                const XSlot *sl = &xl->slot[e & 1][lane];
-                uint32_t seen;
-                unsigned long long t0 = 0;
-                unsigned spins = 0;
-                while (true) {
-                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(&sl->epoch) : "memory");
-                    if (seen == e) break;
-                    if ((++spins & 0xff) == 0) {                           // a rank that never arrives must not wedge the GPU
-                        unsigned long long now;
-                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                        if (t0 == 0) t0 = now;
-                        else if (now - t0 > 10000000000ull) __trap();
+                const unsigned long long *slots[2] = {&xl->xmax[x_epoch & 1][lane], &xl->npos[x_epoch & 1][lane]};
+                unsigned long long got[2];
+                for (int q = 0; q < 2; ++q) {
+                    unsigned long long t0 = 0;
+                    unsigned spins = 0;
+                    while (true) {
+                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got[q]) : "l"(slots[q]) : "memory");
+                        if ((uint32_t)(got[q] >> 32) == x_epoch) break;
+                        if ((++spins & 0xff) == 0 && a.x.timeout_ns) {     // a rank that never arrives must not wedge the GPU
+                            unsigned long long now;
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                            if (t0 == 0) t0 = now;
+                            else if (now - t0 > a.x.timeout_ns) __trap();
+                        }
                     }
                 }
-                mo = *reinterpret_cast<const volatile uint32_t *>(&sl->conf_max_ord);
-                nt = *reinterpret_cast<const volatile int32_t *>(&sl->num_pos);
+                mo = (uint32_t)got[0]; nt = (int)(uint32_t)got[1];
             }
 #pragma unroll
             for (int o = 16; o; o >>= 1) { mo = max(mo, __shfl_xor_sync(FULL, mo, o)); nt += __shfl_xor_sync(FULL, nt, o); }
@@ -263,6 +265,7 @@ __global__ void __launch_bounds__(LOSS_NT, 4) loss_kernel(LossArgs a) {
             a.losses[0] = __fdiv_rn((float)l, (float)n_total);        // multibox_loss.py:117-119
             a.losses[1] = __fdiv_rn((float)c, (float)n_total);
             a.stats[2] = 0;
+            if (a.x.world > 0) *reinterpret_cast<volatile uint32_t *>(&a.x.peers[a.x.rank]->epoch) = x_epoch;   // the step is complete
         }
     }
     GSSD_PHASE(loss, 4, dbg);

@@ -317,21 +317,20 @@ __global__ void __launch_bounds__(MATCH_NT, GSSD_MATCH_MIN_CTAS) match_kernel(Ma
     if (a.x.world > 0) {
         __syncthreads();
         if (s_is_last && warp == 0) {
-            // one lane per peer: statistics, one system-scope fence, then the epoch tag — the peers' stage 2 polls the tag
+            // one lane per peer: both statistics, each tagged with the step's epoch inside its own 64-bit word (common.cuh: XBuf)
             XBuf *xl = a.x.peers[a.x.rank];
             __threadfence();
             const uint32_t mo = atomicMax(&a.stats[0], 0u);
             const int np = atomicAdd(reinterpret_cast<int *>(&a.stats[1]), 0);
-            const uint32_t e = *reinterpret_cast<volatile uint32_t *>(&xl->epoch) + 1;
+            const uint32_t e = *reinterpret_cast<volatile uint32_t *>(&xl->epoch) + 1;      // advanced by stage 2's last CTA
             if (lane < a.x.world) {
-                XSlot *dst = &a.x.peers[lane]->slot[e & 1][a.x.rank];
-                *reinterpret_cast<volatile uint32_t *>(&dst->conf_max_ord) = mo;
-                *reinterpret_cast<volatile int32_t *>(&dst->num_pos) = np;
-                __threadfence_system();                                   // data before the tag, visible to the peer GPU
-                *reinterpret_cast<volatile uint32_t *>(&dst->epoch) = e;
+                XBuf *dst = a.x.peers[lane];
+                *reinterpret_cast<volatile unsigned long long *>(&dst->xmax[e & 1][a.x.rank]) = ((unsigned long long)e << 32) | mo;
+                *reinterpret_cast<volatile unsigned long long *>(&dst->npos[e & 1][a.x.rank]) = ((unsigned long long)e << 32) | (unsigned)np;
+                __threadfence_system();
             }
             __syncwarp();
-            if (lane == 0) { xl->match_done = 0; *reinterpret_cast<volatile uint32_t *>(&xl->epoch) = e; }
+            if (lane == 0) xl->match_done = 0;
         }
     }
     GSSD_PHASE(match, 3, dbg);

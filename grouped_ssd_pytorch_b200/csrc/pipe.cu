@@ -12,7 +12,7 @@ struct gssd_pipe {
     gssd_pipe_slot slot[8];
     cudaStream_t s_copy, s_main, s_side;
     cudaEvent_t ev_in[8], ev_free[8], ev_side[8], ev_done[8];
-    bool busy[8], begun[8], loss_on[8];
+    bool busy[8], begun[8], loss_on[8], fused[8];
     int g_sum[8], g_max[8];
     int64_t next;
     bool use_x;
@@ -42,7 +42,8 @@ size_t layout_slot(const gssd_pipe_cfg &c, uint8_t *base, gssd_pipe_slot *s) {
     float *out = (float *)take((size_t)c.B * c.C * c.top_k * 5 * 4);
     const size_t ws_bytes = gssd_workspace_bytes(GSSD_WS_LOSS, c.B, c.P, c.C, c.max_gt_rows, 0);
     void *ws = take(ws_bytes);
-    if (s) *s = gssd_pipe_slot{loc, conf, scores, gt, gt_off, tags, stats, losses, grad_loc, grad_conf, out, ws, ws_bytes};
+    void *fstate = take(gssd_fused_state_bytes());
+    if (s) *s = gssd_pipe_slot{loc, conf, scores, gt, gt_off, tags, stats, losses, grad_loc, grad_conf, out, ws, ws_bytes, fstate};
     return off;
 }
 
@@ -54,8 +55,10 @@ int64_t cuda_err(cudaError_t e) { return -(1000 + (int64_t)e); }
 #define PIPE_RC(expr) do { int _rc = (expr); if (_rc != 0) return _rc < 0 ? (int64_t)_rc : cuda_err((cudaError_t)_rc); } while (0)
 
 // H2D of one step's inputs + matching + Detect (+ its D2H): everything that does not need the global statistics
+// two_stage: matching is launched here and the loss in finish_step (the caller all-gathers the statistics in between);
+// otherwise finish_step runs the whole loss as one launch when the batch has a one-launch form (fused.cu)
 int64_t begin_step(gssd_pipe *p, const float *loc_h, const float *conf_h, const float *scores_h, const float *gt_h,
-                   const int32_t *gt_off_h, int sum_g, int g_max, float *det_h) {
+                   const int32_t *gt_off_h, int sum_g, int g_max, float *det_h, bool two_stage) {
     const gssd_pipe_cfg &c = p->cfg;
     // gt_h == NULL: a Detect-only step (inference, ssd_multiphase_custom_group.py:384-390) — no matching, no loss
     const bool do_loss = gt_h != nullptr;
@@ -99,7 +102,8 @@ int64_t begin_step(gssd_pipe *p, const float *loc_h, const float *conf_h, const 
     }
     PIPE_CUDA(cudaEventRecord(p->ev_in[k], p->s_copy));
     PIPE_CUDA(cudaStreamWaitEvent(p->s_main, p->ev_in[k], 0));
-    if (!do_loss) {
+    const bool fused = do_loss && !two_stage && gssd_mbox_fused_supported(c.B, c.P, c.C, g_max) != 0;
+    if (!do_loss || fused) {
     } else if (p->use_x)
         PIPE_RC(gssd_mbox_match_x(p->priors, c.P, s.conf, c.C, s.gt, s.gt_off, c.B, sum_g, g_max, c.match_thresh, s.tags, s.stats, &p->x, p->s_main));
     else
@@ -115,7 +119,7 @@ int64_t begin_step(gssd_pipe *p, const float *loc_h, const float *conf_h, const 
         PIPE_CUDA(cudaMemcpyAsync(det_h, s.detect_out, (size_t)c.B * c.C * c.top_k * 5 * 4, cudaMemcpyDeviceToHost, p->s_side));
     }
     PIPE_CUDA(cudaEventRecord(p->ev_side[k], p->s_side));
-    p->g_sum[k] = sum_g; p->g_max[k] = g_max; p->begun[k] = true; p->loss_on[k] = do_loss;
+    p->g_sum[k] = sum_g; p->g_max[k] = g_max; p->begun[k] = true; p->loss_on[k] = do_loss; p->fused[k] = fused;
     p->next = ticket + 1;
     return ticket;
 }
@@ -128,7 +132,11 @@ int64_t finish_step(gssd_pipe *p, int64_t ticket, const gssd_loss_stats *global_
     if (p->loss_on[k] && !losses_h) return GSSD_ERR_ARG;
     const gssd_pipe_slot &s = p->slot[k];
     if (!p->loss_on[k]) {
-    } else if (p->use_x && global_stats == nullptr)
+    } else if (p->fused[k])
+        PIPE_RC(gssd_mbox_loss_fused(s.loc, s.conf, p->priors, c.B, c.P, c.C, s.gt, s.gt_off, p->g_sum[k], p->g_max[k], c.match_thresh,
+                                     c.negpos_ratio, c.var0, c.var1, s.fused_state, p->use_x ? &p->x : nullptr, s.losses, s.grad_loc,
+                                     s.grad_conf, nullptr, nullptr, nullptr, s.ws, s.ws_bytes, p->s_main));
+    else if (p->use_x && global_stats == nullptr)
         PIPE_RC(gssd_mbox_loss_x(s.loc, s.conf, p->priors, c.B, c.P, c.C, s.gt, s.gt_off, p->g_sum[k], p->g_max[k], s.tags, s.stats,
                                  &p->x, c.negpos_ratio, c.var0, c.var1, s.losses, s.grad_loc, s.grad_conf, nullptr, nullptr,
                                  s.ws, s.ws_bytes, p->s_main));
@@ -168,7 +176,8 @@ extern "C" int gssd_pipe_create(gssd_pipe **out, const gssd_pipe_cfg *cfg, const
     cudaError_t e = cudaSuccess;
     for (int k = 0; k < cfg->depth; ++k) {
         layout_slot(*cfg, base + per * k, &p->slot[k]);
-        p->busy[k] = p->begun[k] = p->loss_on[k] = false;
+        p->busy[k] = p->begun[k] = p->loss_on[k] = p->fused[k] = false;
+        if (e == cudaSuccess) e = cudaMemset(p->slot[k].fused_state, 0, gssd_fused_state_bytes());
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_main, cudaStreamNonBlocking);
@@ -218,7 +227,7 @@ extern "C" int gssd_pipe_slot_info(const gssd_pipe *p, int slot, gssd_pipe_slot 
 extern "C" int64_t gssd_pipe_submit(gssd_pipe *p, const float *loc_h, const float *conf_h, const float *scores_h, const float *gt_h,
                                     const int32_t *gt_off_h, int sum_g, int g_max, float *losses_h, float *det_h) {
     if (!p) return GSSD_ERR_ARG;
-    const int64_t t = begin_step(p, loc_h, conf_h, scores_h, gt_h, gt_off_h, sum_g, g_max, det_h);
+    const int64_t t = begin_step(p, loc_h, conf_h, scores_h, gt_h, gt_off_h, sum_g, g_max, det_h, false);
     if (t < 0) return t;
     const int64_t rc = finish_step(p, t, nullptr, 0, losses_h);
     return rc < 0 ? rc : t;
@@ -227,7 +236,7 @@ extern "C" int64_t gssd_pipe_submit(gssd_pipe *p, const float *loc_h, const floa
 extern "C" int64_t gssd_pipe_begin(gssd_pipe *p, const float *loc_h, const float *conf_h, const float *scores_h, const float *gt_h,
                                    const int32_t *gt_off_h, int sum_g, int g_max, float *det_h, void **stream_out) {
     if (!p) return GSSD_ERR_ARG;
-    const int64_t t = begin_step(p, loc_h, conf_h, scores_h, gt_h, gt_off_h, sum_g, g_max, det_h);
+    const int64_t t = begin_step(p, loc_h, conf_h, scores_h, gt_h, gt_off_h, sum_g, g_max, det_h, true);
     if (t >= 0 && stream_out) *stream_out = (void *)p->s_main;
     return t;
 }

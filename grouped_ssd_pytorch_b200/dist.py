@@ -103,14 +103,30 @@ def _hostname():
     return socket.gethostname()
 
 
-def peer_exchange(group=None):
-    """the PeerExchange of `group` (created on first use), or None when the exchange is off or unavailable:
-    GSSD_PEER_XCHG=0, a non-NCCL backend, ranks on several hosts, or no peer access between the GPUs."""
+def _group_key(dist, group):
+    """the process-group OBJECT (kept referenced by the cache, so its id cannot be recycled): a group that is destroyed and
+    created again is a different object and gets fresh IPC mappings"""
+    return dist.group.WORLD if group is None else group
+
+
+def exchange_timeout_ms():
+    """GSSD_XCHG_TIMEOUT_S (default 10): how long a kernel waits for a peer's statistics before it traps.  A rank that never
+    arrives must not wedge the GPU, but a job whose ranks can be further apart than this when they reach the criterion (a
+    stalled data loader, validation on one rank) must raise it, or pass process_group=False for rank-local calls; 0 = for ever."""
+    import os
+    return int(float(os.environ.get("GSSD_XCHG_TIMEOUT_S", "10")) * 1000)
+
+
+def peer_exchange(group=None, owner=None):
+    """the PeerExchange of (`group`, `owner`) (created on first use — a collective over the group), or None when the exchange
+    is off or unavailable: GSSD_PEER_XCHG=0, a non-NCCL backend, ranks on several hosts, or no peer access between the GPUs.
+    Every consumer (a MultiBoxLoss module, a HostPipeline) passes itself as `owner` and gets its OWN buffer and epoch: two
+    consumers that share one would interleave their steps' statistics."""
     import os
     dist, ws, _ = world(group)
     if ws <= 1 or os.environ.get("GSSD_PEER_XCHG", "1") == "0" or not torch.cuda.is_available():
         return None
-    key = id(group) if group is not None else 0
+    key = (_group_key(dist, group), id(owner) if owner is not None else 0)
     if key not in _exchanges:
         ex = None
         if dist.get_backend(group) == "nccl":                    # the same answer on every rank
@@ -124,15 +140,20 @@ def peer_exchange(group=None):
             if int(ok) == 0:
                 ex.close()
                 ex = None
-        _exchanges[key] = ex
-    return _exchanges[key]
+            else:
+                ex.x.timeout_ms = exchange_timeout_ms()
+        _exchanges[key] = (ex, owner)                            # the owner stays referenced: its id cannot be recycled either
+    return _exchanges[key][0]
 
 
-def close_exchanges():
-    for ex in _exchanges.values():
-        if ex is not None:
-            ex.close()
-    _exchanges.clear()
+def close_exchanges(group=None):
+    """tear the exchanges down (all of them, or those of one group): call before destroy_process_group()"""
+    dist, _, _ = world(group)
+    for key in list(_exchanges):
+        if group is None or (dist is not None and key[0] is _group_key(dist, group)):
+            ex = _exchanges.pop(key)[0]
+            if ex is not None:
+                ex.close()
 
 
 # ---- host mirrors of the device encodings (used by the tests and by tools) -----------------------------

@@ -16,33 +16,19 @@ class _MultiBoxLossFn(torch.autograd.Function):
     are 1, i.e. `(loss_l + loss_c).backward()`, train_lesion_multiphase_v2.py:247-248)."""
 
     @staticmethod
-    def forward(ctx, loc, conf, priors, gt, gt_off, sum_g, g_max, threshold, negpos_ratio, variance, masks, group):
+    def forward(ctx, loc, conf, priors, gt, gt_off, sum_g, g_max, threshold, negpos_ratio, variance, masks, group, owner):
+        import ctypes
         lib = _lib.require_cuda()
         dev = loc.device
         B, P, C = conf.shape
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         st = _lib.stream()
-        tags = torch.empty((B, P), dtype=torch.int16, device=dev)
-        stats = torch.empty((_lib.STATS_HEADER_BYTES + 4 * B,), dtype=torch.uint8, device=dev)
         # DataParallel semantics of the reference: x_max and N are over the GLOBAL batch
-        # (train_lesion_multiphase_v2.py:242-246 -> multibox_loss.py:117, box_utils.py:167): the 16-byte statistics of
-        # every rank travel either through the peer exchange (NVLink peer stores from stage 1's last CTA) or through
-        # an all-gather between the stages.
-        gstats, n_g = None, 0
+        # (train_lesion_multiphase_v2.py:242-246 -> multibox_loss.py:117, box_utils.py:167): the statistics of every rank
+        # travel either through the peer exchange (NVLink peer stores issued by the kernels) or through an all-gather
+        # between the two stages.
         _, world, _ = gdist.world(group)
-        ex = gdist.peer_exchange(group) if world > 1 else None
-        if ex is not None:
-            import ctypes
-            _lib.check(lib.gssd_mbox_match_x(priors.data_ptr(), P, conf.data_ptr(), C, gt.data_ptr(), gt_off.data_ptr(),
-                                             B, sum_g, g_max, float(threshold), tags.data_ptr(), stats.data_ptr(),
-                                             ctypes.byref(ex.x), st), "gssd_mbox_match_x")
-        else:
-            _lib.check(lib.gssd_mbox_match(priors.data_ptr(), P, conf.data_ptr(), C, gt.data_ptr(), gt_off.data_ptr(),
-                                           B, sum_g, g_max, float(threshold), tags.data_ptr(), stats.data_ptr(), st),
-                       "gssd_mbox_match")
-        if world > 1 and ex is None:
-            gstats = gdist.all_gather_headers(stats[:_lib.STATS_HEADER_BYTES], group)
-            n_g = world
+        ex = gdist.peer_exchange(group, owner=owner) if world > 1 else None
         losses = torch.empty((2,), dtype=torch.float32, device=dev)
         grad_loc = torch.empty_like(loc) if need_grad else None
         grad_conf = torch.empty_like(conf) if need_grad else None
@@ -50,21 +36,49 @@ class _MultiBoxLossFn(torch.autograd.Function):
         neg = torch.empty((B, P), dtype=torch.uint8, device=dev) if masks else None
         ws_bytes = lib.gssd_workspace_bytes(_lib.WS_LOSS, B, P, C, sum_g, 0)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-        if ex is not None:
-            _lib.check(lib.gssd_mbox_loss_x(loc.data_ptr(), conf.data_ptr(), priors.data_ptr(), B, P, C,
-                                            gt.data_ptr(), gt_off.data_ptr(), sum_g, g_max, tags.data_ptr(), stats.data_ptr(),
-                                            ctypes.byref(ex.x), int(negpos_ratio), float(variance[0]), float(variance[1]),
-                                            losses.data_ptr(), _lib.ptr(grad_loc), _lib.ptr(grad_conf),
-                                            _lib.ptr(pos), _lib.ptr(neg), ws.data_ptr(), ws_bytes, st), "gssd_mbox_loss_x")
+        var0, var1 = float(variance[0]), float(variance[1])
+        one_launch = (world == 1 or ex is not None) and lib.gssd_mbox_fused_supported(B, P, C, g_max) != 0
+        if one_launch:
+            # the whole forward + backward as ONE launch (csrc/fused.cu): every CTA of the batch is resident at once
+            num_pos = torch.empty((B,), dtype=torch.int32, device=dev)
+            state = _lib.fused_state(dev, st)
+            _lib.check(lib.gssd_mbox_loss_fused(loc.data_ptr(), conf.data_ptr(), priors.data_ptr(), B, P, C,
+                                                gt.data_ptr(), gt_off.data_ptr(), sum_g, g_max, float(threshold),
+                                                int(negpos_ratio), var0, var1, state.data_ptr(),
+                                                ctypes.byref(ex.x) if ex is not None else None,
+                                                losses.data_ptr(), _lib.ptr(grad_loc), _lib.ptr(grad_conf),
+                                                _lib.ptr(pos), _lib.ptr(neg), num_pos.data_ptr(), ws.data_ptr(), ws_bytes, st),
+                       "gssd_mbox_loss_fused")
         else:
-            _lib.check(lib.gssd_mbox_loss(loc.data_ptr(), conf.data_ptr(), priors.data_ptr(), B, P, C,
-                                          gt.data_ptr(), gt_off.data_ptr(), sum_g, g_max, tags.data_ptr(), stats.data_ptr(),
-                                          _lib.ptr(gstats), n_g, int(negpos_ratio), float(variance[0]), float(variance[1]),
-                                          losses.data_ptr(), _lib.ptr(grad_loc), _lib.ptr(grad_conf),
-                                          _lib.ptr(pos), _lib.ptr(neg), ws.data_ptr(), ws_bytes, st), "gssd_mbox_loss")
+            tags = torch.empty((B, P), dtype=torch.int16, device=dev)
+            stats = torch.empty((_lib.STATS_HEADER_BYTES + 4 * B,), dtype=torch.uint8, device=dev)
+            gstats, n_g = None, 0
+            if ex is not None:
+                _lib.check(lib.gssd_mbox_match_x(priors.data_ptr(), P, conf.data_ptr(), C, gt.data_ptr(), gt_off.data_ptr(),
+                                                 B, sum_g, g_max, float(threshold), tags.data_ptr(), stats.data_ptr(),
+                                                 ctypes.byref(ex.x), st), "gssd_mbox_match_x")
+            else:
+                _lib.check(lib.gssd_mbox_match(priors.data_ptr(), P, conf.data_ptr(), C, gt.data_ptr(), gt_off.data_ptr(),
+                                               B, sum_g, g_max, float(threshold), tags.data_ptr(), stats.data_ptr(), st),
+                           "gssd_mbox_match")
+            if world > 1 and ex is None:
+                gstats = gdist.all_gather_headers(stats[:_lib.STATS_HEADER_BYTES], group)
+                n_g = world
+            if ex is not None:
+                _lib.check(lib.gssd_mbox_loss_x(loc.data_ptr(), conf.data_ptr(), priors.data_ptr(), B, P, C,
+                                                gt.data_ptr(), gt_off.data_ptr(), sum_g, g_max, tags.data_ptr(), stats.data_ptr(),
+                                                ctypes.byref(ex.x), int(negpos_ratio), var0, var1,
+                                                losses.data_ptr(), _lib.ptr(grad_loc), _lib.ptr(grad_conf),
+                                                _lib.ptr(pos), _lib.ptr(neg), ws.data_ptr(), ws_bytes, st), "gssd_mbox_loss_x")
+            else:
+                _lib.check(lib.gssd_mbox_loss(loc.data_ptr(), conf.data_ptr(), priors.data_ptr(), B, P, C,
+                                              gt.data_ptr(), gt_off.data_ptr(), sum_g, g_max, tags.data_ptr(), stats.data_ptr(),
+                                              _lib.ptr(gstats), n_g, int(negpos_ratio), var0, var1,
+                                              losses.data_ptr(), _lib.ptr(grad_loc), _lib.ptr(grad_conf),
+                                              _lib.ptr(pos), _lib.ptr(neg), ws.data_ptr(), ws_bytes, st), "gssd_mbox_loss")
+            num_pos = stats[_lib.STATS_HEADER_BYTES:].view(torch.int32)
         ctx.grads = (grad_loc, grad_conf)
         ctx.set_materialize_grads(False)       # no zero tensors for the outputs nobody differentiates (num_pos, an unused loss)
-        num_pos = stats[_lib.STATS_HEADER_BYTES:].view(torch.int32)
         aux = [t for t in (pos, neg, num_pos) if t is not None]
         ctx.mark_non_differentiable(*aux)
         return losses[0], losses[1], pos, neg, num_pos
@@ -82,7 +96,7 @@ class _MultiBoxLossFn(torch.autograd.Function):
                                "through both losses; differentiate loss_l and loss_c separately, or call forward again")
         grad_loc, grad_conf = ctx.grads
         if grad_loc is None:
-            return (None,) * 12
+            return (None,) * 13
         lib = _lib.load()
         dev = grad_loc.device
 
@@ -93,13 +107,13 @@ class _MultiBoxLossFn(torch.autograd.Function):
             if g_l is None or g_c is None:     # one loss only: out of place, the buffers stay valid for the other one
                 out_l = grad_loc * scalar(g_l) if g_l is not None else None
                 out_c = grad_conf * scalar(g_c) if g_c is not None else None
-                return (out_l, out_c) + (None,) * 10
+                return (out_l, out_c) + (None,) * 11
             ctx.grads = None                   # hand the buffers over: autograd can adopt them without a copy
             g_l, g_c = scalar(g_l), scalar(g_c)
             _lib.check(lib.gssd_mbox_scale_grads(grad_loc.data_ptr(), grad_loc.numel(), grad_conf.data_ptr(),
                                                  grad_conf.numel(), g_l.data_ptr(), g_c.data_ptr(), _lib.stream()),
                        "gssd_mbox_scale_grads")
-        return (grad_loc, grad_conf) + (None,) * 10
+        return (grad_loc, grad_conf) + (None,) * 11
 
 
 class MultiBoxLoss(nn.Module):
@@ -167,7 +181,7 @@ class MultiBoxLoss(nn.Module):
                 targets if not isinstance(targets, (list, tuple)) else [targets[i] for i in range(num)], dev)
             loss_l, loss_c, pos, neg, num_pos = _MultiBoxLossFn.apply(
                 loc, conf, pri, gt, gt_off, sum_g, g_max, self.threshold, self.negpos_ratio, self.variance,
-                self.keep_masks, self.process_group)
+                self.keep_masks, self.process_group, self)
             if self.keep_masks:
                 self.last_masks = dict(pos=pos, neg=neg, num_pos=num_pos)
         if out_dev != dev:

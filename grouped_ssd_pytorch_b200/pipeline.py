@@ -69,7 +69,7 @@ class HostPipeline(object):
         self.group = process_group
         self._gathered = None
         _, world, _ = gdist.world(process_group)
-        self._ex = gdist.peer_exchange(process_group) if world > 1 else None
+        self._ex = gdist.peer_exchange(process_group, owner=self) if world > 1 else None
         if self._ex is not None:                                  # statistics over NVLink peer memory: one native call per step
             _lib.check(lib.gssd_pipe_set_xchg(h, C.byref(self._ex.x)), "gssd_pipe_set_xchg")
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GSSD_ABI_VERSION 1
+#define GSSD_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define GSSD_API __attribute__((visibility("default")))
@@ -45,6 +45,7 @@ extern "C" {
 #define GSSD_ERR_WS     -3   /* workspace smaller than gssd_workspace_bytes() */
 #define GSSD_ERR_VALUE  -4   /* reference-visible ValueError (variance <= 0, nms_thresh <= 0) */
 #define GSSD_ERR_EMPTY  -5   /* an image without ground truth (reference: IndexError) */
+#define GSSD_ERR_UNSUPPORTED -6  /* this shape has no one-launch form (gssd_mbox_loss_fused): use the two stages */
 
 #define GSSD_MAX_GT_PER_IMAGE   128    /* G per image held in shared memory */
 #define GSSD_MAX_PRIORS       49152    /* P: keys of one image must fit one SM's shared memory */
@@ -178,6 +179,10 @@ GSSD_API int gssd_mbox_loss(const float *loc, const float *conf, const float *pr
 typedef struct gssd_xchg {
     void   *peers[GSSD_XCHG_MAX_RANKS];   /* device pointers to the exchange buffer of every rank (own included) */
     int32_t rank, world;
+    uint32_t timeout_ms;                  /* a kernel that waits longer than this for a peer's statistics traps instead of
+                                             wedging the GPU; 0 = wait for ever.  Size it for the longest time two ranks can
+                                             be apart when they reach the criterion (a stalled data loader counts) */
+    uint32_t reserved;
 } gssd_xchg;
 /* allocate (cudaMalloc) and zero this rank's exchange buffer; export it for the peers (cudaIpcMemHandle_t) */
 GSSD_API int gssd_xchg_create(void **xbuf_out, void *ipc_handle_out_host /* 64 bytes */);
@@ -196,6 +201,24 @@ GSSD_API int gssd_mbox_loss_x(const float *loc, const float *conf, const float *
                      float *losses, float *grad_loc, float *grad_conf,
                      uint8_t *pos_mask, uint8_t *neg_mask,
                      void *ws, size_t ws_bytes, void *stream);
+
+/* MultiBoxLoss.forward (multibox_loss.py:46-120, matching included) and the gradients of its two outputs in ONE launch,
+ * for batches whose CTAs are all resident at once (the reference's training batch of 32 is): the two batch-wide scalars
+ * meet at two counters in global memory instead of at a kernel boundary, and conf is read from HBM once.
+ *   state: gssd_fused_state_bytes() bytes of device memory, zeroed ONCE by the caller and then reused by launches that are
+ *          ordered on one stream (the kernel resets it on its way out);  x_host: peer exchange of a data-parallel job or NULL;
+ *   num_pos[B] int32 optional;  ws: gssd_workspace_bytes(GSSD_WS_LOSS, ...);  everything else as gssd_mbox_loss.
+ * Returns GSSD_ERR_UNSUPPORTED when the shape cannot be co-resident (ask gssd_mbox_fused_supported first, or fall back to
+ * gssd_mbox_match + gssd_mbox_loss: same results bit for bit). */
+GSSD_API size_t gssd_fused_state_bytes(void);
+GSSD_API int gssd_mbox_fused_supported(int B, int P, int C, int g_max);
+GSSD_API int gssd_mbox_loss_fused(const float *loc, const float *conf, const float *priors, int B, int P, int C,
+                         const float *gt, const int32_t *gt_off, int sum_G, int g_max,
+                         float threshold, int negpos_ratio, float var0, float var1,
+                         void *state, const gssd_xchg *x_host,
+                         float *losses, float *grad_loc, float *grad_conf,
+                         uint8_t *pos_mask, uint8_t *neg_mask, int32_t *num_pos,
+                         void *ws, size_t ws_bytes, void *stream);
 
 /* Backward helper: grad_loc *= g[0], grad_conf *= g[1] in place (g = upstream gradients of the two
  * scalar losses, device).  Touches no memory when g == (1,1), the `(loss_l+loss_c).backward()` case
@@ -320,6 +343,7 @@ typedef struct gssd_pipe_slot {                       /* device buffers of one i
     float *losses, *grad_loc, *grad_conf, *detect_out;
     void *ws;
     size_t ws_bytes;
+    void *fused_state;                                /* gssd_fused_state_bytes(): rendezvous state of the one-launch loss */
 } gssd_pipe_slot;
 
 GSSD_API size_t  gssd_pipe_arena_bytes(const gssd_pipe_cfg *cfg_host);

@@ -37,7 +37,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     lib = ctypes.CDLL(path)
     for s in declared_symbols():
         assert hasattr(lib, s), "libgssd_b200.so does not export " + s
-    assert lib.gssd_abi_version() == 1
+    assert lib.gssd_abi_version() == 2
     out = subprocess.check_output(["nm", "-D", "--defined-only", path], text=True)
     exported = set(re.findall(r" T (\w+)", out))
     extra = {e for e in exported if not e.startswith("gssd_")}

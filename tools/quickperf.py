@@ -57,20 +57,28 @@ def run(pname, B, gmax):
     def k_loss(i):
         _lib.check(lib.gssd_mbox_loss(locs[i].data_ptr(), confs[i].data_ptr(), pri.data_ptr(), B, P, 2, gt.data_ptr(), gt_off.data_ptr(), sum_g, g_max, tags.data_ptr(), stats.data_ptr(), None, 0, 3, 0.1, 0.2, losses.data_ptr(), gl[i].data_ptr(), gc[i].data_ptr(), None, None, ws.data_ptr(), wsb, st))
 
+    state = torch.zeros(64, dtype=torch.uint8, device=dev)
+    npos = torch.empty(B, dtype=torch.int32, device=dev)
+    fused_ok = lib.gssd_mbox_fused_supported(B, P, 2, g_max) == 1
+
+    def k_fused(i):
+        _lib.check(lib.gssd_mbox_loss_fused(locs[i].data_ptr(), confs[i].data_ptr(), pri.data_ptr(), B, P, 2, gt.data_ptr(), gt_off.data_ptr(), sum_g, g_max, 0.5, 3, 0.1, 0.2, state.data_ptr(), None, losses.data_ptr(), gl[i].data_ptr(), gc[i].data_ptr(), None, None, npos.data_ptr(), ws.data_ptr(), wsb, st))
+
     def k_det(i):
         _lib.check(lib.gssd_detect_logits(locs[i].data_ptr(), confs[i].data_ptr(), bias, pri.data_ptr(), B, P, 2, 200, 0.2, 0.45, 0.1, 0.2, out.data_ptr(), None, None, st))
 
     k_match(0)
     tm, tl, td = timeit(k_match, n_sets), timeit(k_loss, n_sets), timeit(k_det, n_sets)
+    tf = timeit(k_fused, n_sets) if fused_ok else float("nan")
     bl, bd = B * P * 64, B * (P * 40 + 8000)
-    print("%-8s B=%4d G<=%2d  match %7.1f us | loss %7.1f us (%5.0f GB/s, %4.1f%%) | match+loss %5.1f%% | detect %7.1f us (%5.0f GB/s, %4.1f%%)" % (
-        pname, B, gmax, tm, tl, bl / tl / 1e3, bl / tl / 1e3 / HBM * 100, bl / (tm + tl) / 1e3 / HBM * 100, td, bd / td / 1e3, bd / td / 1e3 / HBM * 100), flush=True)
+    print("%-8s B=%4d G<=%2d  match %7.1f us | loss %7.1f us (%5.0f GB/s, %4.1f%%) | match+loss %5.1f%% | ONE LAUNCH %7.1f us (%4.1f%%) | detect %7.1f us (%5.0f GB/s, %4.1f%%)" % (
+        pname, B, gmax, tm, tl, bl / tl / 1e3, bl / tl / 1e3 / HBM * 100, bl / (tm + tl) / 1e3 / HBM * 100, tf, bl / tf / 1e3 / HBM * 100, td, bd / td / 1e3, bd / td / 1e3 / HBM * 100), flush=True)
 
 
 if __name__ == "__main__":
     if os.environ.get("QP_ONLY"):             # one configuration, several repeats (A/B runs of library variants)
         for _ in range(3):
-            run("v2", int(os.environ["QP_ONLY"]), 5)
+            run(os.environ.get("QP_PRIORS", "v2"), int(os.environ["QP_ONLY"]), int(os.environ.get("QP_GMAX", "5")))
         sys.exit(0)
     for pname, B, g in [("v2", 32, 5), ("v2", 64, 5), ("v2", 256, 5), ("v2", 1024, 5), ("v2_512", 64, 32), ("v2_512", 512, 32)]:
         run(pname, B, g)
