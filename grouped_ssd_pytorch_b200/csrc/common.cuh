@@ -93,11 +93,15 @@ static inline int resident_ctas(const void *kern, int threads, size_t smem) {
 // ---- peer exchange of the loss statistics (gssd_xchg, include/gssd.h) ---------------------------------------
 // One 64-bit word per (value, step parity, source rank): (epoch << 32) | value.  Value and tag travel in ONE naturally
 // aligned 8-byte store, so a reader that sees the epoch of the current step also sees the value — no fence between them.
+constexpr int GSSD_FUSED_MAX_CTAS = 1024;    // CTAs of one rank's one-launch loss kernel (fused.cu) that have a slot
 struct XBuf {
-    unsigned long long xmax[2][GSSD_XCHG_MAX_RANKS];   // max of conf (ordered uint32) of every rank
-    unsigned long long npos[2][GSSD_XCHG_MAX_RANKS];   // number of positives of every rank
+    unsigned long long xmax[2][GSSD_XCHG_MAX_RANKS];   // max of conf (ordered uint32) of every rank   (two-launch path)
+    unsigned long long npos[2][GSSD_XCHG_MAX_RANKS];   // number of positives of every rank           (two-launch path)
     uint32_t epoch;                          // completed steps (advanced by the LAST CTA of a step's last kernel)
     uint32_t match_done;                     // CTA counter of the running stage-1 kernel (two-launch path)
+    // one-launch path: every CTA of every rank owns a word per value; hdr = how many CTAs that rank runs this step
+    unsigned long long hdr[2][GSSD_XCHG_MAX_RANKS];
+    unsigned long long slot[2][2][GSSD_XCHG_MAX_RANKS][GSSD_FUSED_MAX_CTAS];   // [parity][0: conf max, 1: positives][rank][cta]
 };
 struct XDev {                                // kernel-argument image of gssd_xchg
     XBuf *peers[GSSD_XCHG_MAX_RANKS];
@@ -114,8 +118,13 @@ static inline XDev xdev_from(const gssd_xchg *x) {
     return d;
 }
 
-// rendezvous state of the one-launch MultiBoxLoss (fused.cu): zero-initialised once, reset by the last CTA of every launch
-struct FusedState { uint32_t bar1, bar2, xmax_ord; int32_t n_pos; uint32_t done; uint32_t pad[3]; };
+// rendezvous state of the one-launch MultiBoxLoss (fused.cu) on ONE GPU: zero-initialised once.  Every CTA owns a word per
+// value, (epoch << 32) | value, written with one plain store and polled by the readers: no atomics, no fences, nothing to
+// reset (the epoch, advanced by the last CTA to leave, tells the launches apart).
+struct FusedState {
+    uint32_t epoch; uint32_t pad[3];
+    unsigned long long slot[4][GSSD_FUSED_MAX_CTAS];    // [0: conf max, 1: positives, 2: loss_l partial, 3: loss_c partial][cta]
+};
 
 // ---- optional phase timing (debug build only: -DGSSD_PHASE_TIMING, see tools/phase_times.py) ----------
 #ifdef GSSD_PHASE_TIMING

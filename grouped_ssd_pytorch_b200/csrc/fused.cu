@@ -5,16 +5,18 @@
 // (match.cu then loss.cu) spend more time starting, draining and handing 16 bytes of statistics through global memory than
 // moving data.  The only batch-wide dependencies of the loss are two scalars — the max of conf (box_utils.py:167) and the
 // number of positives N (multibox_loss.py:117) — so all CTAs of the batch are made co-resident (cooperative launch) and
-// meet at two counters in global memory; everything else is per image and stays inside one thread-block cluster.
+// meet twice through global memory: every CTA owns one word per value, (epoch << 32) | value, which it writes with a plain
+// store and everybody polls — no atomics, no fences, nothing to reset; everything else is per image and stays inside one
+// thread-block cluster.
 //
 // Per image: a cluster of S CTAs of NT threads; the priors are dealt to the CTAs in interleaved chunks of 256 (CTA r owns
 // chunks r, r+S, ...: the large priors at the end of the list overlap most GT boxes, contiguous slices would leave the first
 // CTAs waiting).  A thread owns the same priors in every phase, and the CTA keeps their conf rows, tags and mining keys in
 // shared memory: conf is read from HBM exactly once.
 //
-//   A  conf rows -> shared memory (cp.async), local max -> atomicMax; arrive at rendezvous 1
+//   A  conf rows -> shared memory (cp.async), local max -> this CTA's word of rendezvous 1
 //   B  IoU sweep (as match.cu), per-GT best prior combined over the cluster (1 exchange), sequential force match
-//   C  positives counted -> atomicAdd N; arrive at rendezvous 2
+//   C  positives counted -> this CTA's word of rendezvous 2
 //   D  wait for rendezvous 1 (long complete): mining keys with the batch-global max, first radix digit (11 bits) counted
 //      on the fly
 //   E  select of the min(ratio*num_pos, P-1) largest (key, lower index first) composites: the non-empty bins of every CTA
@@ -23,13 +25,13 @@
 //      composites share 11 / 22 / 32 ... leading bits (heavily tied keys) — the composite carries the prior index below the
 //      key, so "more than 256 EQUAL keys" is just two more passes, with no special case
 //   F  wait for rendezvous 2: smooth-L1 + CE over pos | neg, all gradients written (zeros for everybody else)
-//   G  per-CTA partial sums in double; the last CTA to finish reduces them in a fixed order, divides by N, and resets the
-//      rendezvous counters for the next launch
+//   G  per-CTA partial sums in double; the last CTA to finish reduces them in a fixed order, divides by N, and advances the
+//      epoch for the next launch
 //
-// Data-parallel jobs (gssd_xchg): the CTA that completes a rendezvous stores this rank's value, tagged with the step's
-// epoch in the same 64-bit word, into every peer's exchange buffer over NVLink; CTAs then wait on their LOCAL buffer for all
-// ranks' words instead of on the local counter.  The max of conf is published microseconds after the kernel starts and is
-// needed only after the IoU sweep; N is published before the select and needed after it: the exchange latency hides.
+// Data-parallel jobs (gssd_xchg): every CTA stores its two words into the exchange buffer of EVERY rank over NVLink (8 bytes
+// per peer and value) and the readers poll world x CTAs words of their LOCAL buffer: no aggregation step, no collective.  The
+// max of conf is published microseconds after the kernel starts and is needed only after the IoU sweep; the positives are
+// published before the select and needed after it: the exchange latency hides.
 #include <mutex>
 #include <vector>
 
@@ -71,47 +73,23 @@ __device__ __forceinline__ float fsmooth_l1(float d, float &grad) {
     return __fsub_rn(ad, 0.5f);
 }
 
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys64(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// wait for a rendezvous counter of this GPU.  Every CTA is resident (cooperative launch), so this cannot deadlock; the bound
-// (4 s) only turns a broken invariant — e.g. a state buffer shared by launches on two streams — into a trap instead of a hang
-__device__ __forceinline__ void bar_wait(const uint32_t *counter, uint32_t target) {
-    unsigned long long t0 = 0;
-    unsigned spins = 0;
-    while (ld_acquire_gpu(counter) < target) {
-        if ((++spins & 0x3ff) == 0) {
-            unsigned long long now;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000ull) __trap();
-        }
-    }
-}
-
-// wait until every rank's word of this epoch is in the local exchange buffer; lanes < world of one warp; returns the word
-__device__ __forceinline__ unsigned long long xchg_wait(const unsigned long long *slot, uint32_t epoch, unsigned long long timeout_ns) {
+// poll one word until it carries the epoch of this step; returns its value.  Every CTA of every rank is resident while we
+// wait (cooperative launch), so only a rank that never reaches the criterion — or a state buffer shared by launches on two
+// streams — can keep us here: after `timeout_ns` (0 = never) the kernel traps instead of wedging the GPU.
+__device__ __forceinline__ uint32_t slot_wait(const unsigned long long *slot, uint32_t epoch, unsigned long long timeout_ns) {
     unsigned long long v, t0 = 0;
     unsigned spins = 0;
     while (true) {
-        v = ld_acquire_sys64(slot);
+        v = *reinterpret_cast<const volatile unsigned long long *>(slot);
         if ((uint32_t)(v >> 32) == epoch) break;
-        if ((++spins & 0xff) == 0 && timeout_ns) {                 // a rank that never arrives must not wedge the GPU
+        if ((++spins & 0xff) == 0 && timeout_ns) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (t0 == 0) t0 = now;
             else if (now - t0 > timeout_ns) __trap();
         }
     }
-    return v;
+    return (uint32_t)v;
 }
 
 template <int NT, bool C2, bool GRADS>
@@ -140,8 +118,9 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(FusedArgs a) {
     int *glist = sbp + G;
     uint32_t *hist = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(glist + G) + 15) & ~(uintptr_t)15);
     uint32_t *total = hist + FBINS;                                                    // [2][FBINS]
-    unsigned long long *cand = reinterpret_cast<unsigned long long *>(total + 2 * FBINS);
-    uint32_t *keys = reinterpret_cast<uint32_t *>(cand + FCAND);
+    unsigned long long *cand = reinterpret_cast<unsigned long long *>(total + 2 * FBINS);      // [S][FCAND]: one region per CTA of the image
+    unsigned long long *flat = cand + (size_t)S * FCAND;                                       // [FCAND]
+    uint32_t *keys = reinterpret_cast<uint32_t *>(flat + FCAND);
     float *conf_s = reinterpret_cast<float *>(keys + a.items);
     uint16_t *stag = reinterpret_cast<uint16_t *>(conf_s + (size_t)a.items * C);
 
@@ -152,8 +131,8 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(FusedArgs a) {
     __shared__ int s_nlist;
     __shared__ uint32_t s_xmax_ord, s_digit, s_krem, s_eq, s_cand_count, s_wtot[NW];
     __shared__ int s_ntotal, s_npos_img, s_npos_cta;
+    __shared__ uint32_t s_cand_n[8];
     __shared__ unsigned long long s_cut;
-    __shared__ bool s_last;
 
     const int n_chunks = (a.P + FCHUNK - 1) / FCHUNK;
     const int my_chunks = (int)rank < n_chunks ? (n_chunks - (int)rank + (int)S - 1) / (int)S : 0;
@@ -162,9 +141,59 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(FusedArgs a) {
     const bool dbg = blockIdx.x == 0 && blockIdx.y == 0;
     GSSD_PHASE(fused, 0, dbg);
 
-    // epoch of this step in the peer exchange (read before anybody can have advanced it: it moves when the LAST CTA exits)
-    uint32_t epoch = 0;
-    if (a.x.world > 0) epoch = *reinterpret_cast<const volatile uint32_t *>(&a.x.peers[a.x.rank]->epoch) + 1;
+    // epoch of this step (read before anybody can have advanced it: it moves when the LAST CTA of the launch exits)
+    const bool multi = a.x.world > 0;
+    const uint32_t epoch = (multi ? *reinterpret_cast<const volatile uint32_t *>(&a.x.peers[a.x.rank]->epoch)
+                                  : *reinterpret_cast<const volatile uint32_t *>(&a.state->epoch)) + 1;
+    const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
+    // this CTA's word of rendezvous `kind` (0: conf max, 1: positives): one plain 8-byte store per destination
+    auto publish = [&](int kind, uint32_t value) {
+        const unsigned long long word = ((unsigned long long)epoch << 32) | value;
+        if (!multi) {
+            *reinterpret_cast<volatile unsigned long long *>(&a.state->slot[kind][cta]) = word;
+        } else {
+            for (int r = 0; r < a.x.world; ++r) {
+                XBuf *dst = a.x.peers[r];
+                if (kind == 0 && cta == 0)
+                    *reinterpret_cast<volatile unsigned long long *>(&dst->hdr[epoch & 1][a.x.rank]) = ((unsigned long long)epoch << 32) | n_ctas;
+                *reinterpret_cast<volatile unsigned long long *>(&dst->slot[epoch & 1][kind][a.x.rank][cta]) = word;
+            }
+        }
+    };
+    // all words of rendezvous `kind`, combined with MAX (kind 0) or SUM (kind 1) by the whole CTA; result in *s_out
+    auto collect = [&](int kind, uint32_t *s_out) {
+        uint32_t acc = 0;
+        if (!multi) {
+            for (unsigned i = tid; i < n_ctas; i += NT) {
+                const uint32_t v = slot_wait(&a.state->slot[kind][i], epoch, 4000000000ull);
+                acc = kind == 0 ? max(acc, v) : acc + v;
+            }
+        } else {
+            const XBuf *xl = a.x.peers[a.x.rank];
+            for (int r = 0; r < a.x.world; ++r) {
+                const unsigned n_r = slot_wait(&xl->hdr[epoch & 1][r], epoch, a.x.timeout_ns);
+                for (unsigned i = tid; i < n_r; i += NT) {
+                    const uint32_t v = slot_wait(&xl->slot[epoch & 1][kind][r][i], epoch, a.x.timeout_ns);
+                    acc = kind == 0 ? max(acc, v) : acc + v;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const uint32_t t = __shfl_xor_sync(FULL, acc, o);
+            acc = kind == 0 ? max(acc, t) : acc + t;
+        }
+        if (lane == 0) s_wtot[warp] = acc;
+        __syncthreads();
+        acc = lane < NW ? s_wtot[lane] : 0u;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const uint32_t t = __shfl_xor_sync(FULL, acc, o);
+            acc = kind == 0 ? max(acc, t) : acc + t;
+        }
+        if (tid == 0) *s_out = acc;
+        __syncthreads();
+    };
 
     // ---- A. conf rows -> shared memory, asynchronously; buffers of the select cleared; GT staged -------------------------
     for (int cj = 0; cj < my_chunks; ++cj) {
@@ -196,34 +225,38 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(FusedArgs a) {
         sbest[g] = 0x00000000ffffffffull;                        // an all-zero IoU row resolves to prior 0 (torch.max: first maximum)
         glist[g] = g;
     }
+    GSSD_PHASE(fused, 12, dbg);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    if (S > 1) cluster_arrive();         // my receiving buffers are initialised; waited for before the first remote store
+    GSSD_PHASE(fused, 13, dbg);
+    if (S > 1) cluster_arrive();
+    GSSD_PHASE(fused, 14, dbg);         // my receiving buffers are initialised; waited for before the first remote store
 
-    // local max of conf -> batch max (box_utils.py:167), then arrive at rendezvous 1
+    // local max of conf -> batch max (box_utils.py:167): this CTA's word of rendezvous 1.  Only the last chunk of the image can
+    // be partial; the full chunks are one contiguous run of floats in shared memory.
     {
-        float cmax = -INFINITY;
-        for (int cj = 0; cj < my_chunks; ++cj) {
-            const int ck = (int)rank + cj * (int)S;
-            const int nf = min(FCHUNK, a.P - ck * FCHUNK) * C;
-            const float *src = conf_s + (size_t)cj * FCHUNK * C;
-            for (int i = tid; i < nf; i += NT) cmax = fmaxf(cmax, src[i]);
+        const bool owns_tail = my_chunks > 0 && (int)rank + (my_chunks - 1) * (int)S == n_chunks - 1 && (a.P % FCHUNK) != 0;
+        const int n_full4 = (my_chunks - (owns_tail ? 1 : 0)) * FCHUNK * C / 4;              // FCHUNK * C is a multiple of 4
+        const float4 *src4 = reinterpret_cast<const float4 *>(conf_s);
+        float m0 = -INFINITY, m1 = -INFINITY;
+        int i = tid;
+        for (; i + NT < n_full4; i += 2 * NT) {
+            const float4 u = src4[i], v = src4[i + NT];
+            m0 = fmaxf(m0, fmaxf(fmaxf(u.x, u.y), fmaxf(u.z, u.w)));
+            m1 = fmaxf(m1, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
         }
-        cmax = warp_max(cmax);
+        if (i < n_full4) { const float4 u = src4[i]; m0 = fmaxf(m0, fmaxf(fmaxf(u.x, u.y), fmaxf(u.z, u.w))); }
+        if (owns_tail) {
+            const float *src = conf_s + (size_t)(my_chunks - 1) * FCHUNK * C;
+            const int nf = (a.P % FCHUNK) * C;
+            for (int q = tid; q < nf; q += NT) m1 = fmaxf(m1, src[q]);
+        }
+        float cmax = warp_max(fmaxf(m0, m1));
         if (lane == 0) s_wf[warp] = cmax;
         __syncthreads();
-        if (tid == 0) {
-            float mx = -INFINITY;
-            for (int w = 0; w < NW; ++w) mx = fmaxf(mx, s_wf[w]);
-            if (my_chunks > 0) atomicMax(&a.state->xmax_ord, f2ord(mx));
-            __threadfence();
-            const unsigned old = atomicAdd(&a.state->bar1, 1u);
-            if (old == n_ctas - 1 && a.x.world > 0) {            // this rank's max is final: publish it to every rank
-                const unsigned long long word = ((unsigned long long)epoch << 32) | atomicMax(&a.state->xmax_ord, 0u);
-                for (int r = 0; r < a.x.world; ++r)
-                    *reinterpret_cast<volatile unsigned long long *>(&a.x.peers[r]->xmax[epoch & 1][a.x.rank]) = word;
-                __threadfence_system();
-            }
+        if (warp == 0) {
+            cmax = warp_max(lane < NW ? s_wf[lane] : -INFINITY);
+            if (lane == 0) publish(0, my_chunks > 0 ? f2ord(cmax) : 0u);
         }
     }
     GSSD_PHASE(fused, 1, dbg);
@@ -269,12 +302,19 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(FusedArgs a) {
     }
     const int n_list = s_nlist;
     const bool warp_cull = n_list >= 8;
+    auto prior_of = [&](int t) {                                 // clamped: a trip past the end re-reads a cached row
+        const int cj = min(t * SLOTS + (tid >> 8), max(my_chunks - 1, 0));
+        return a.priors[min(((int)rank + cj * (int)S) * FCHUNK + (tid & 255), p_last)];
+    };
+    float4 nxt = prior_of(0);
     for (int t = 0; t < trips; ++t) {
         const int cj = t * SLOTS + (tid >> 8);                   // warp-uniform
+        const float4 cur = nxt;
+        nxt = prior_of(t + 1);                                   // in flight while this trip's pairs are swept
         if (cj >= my_chunks) continue;
         const int p = ((int)rank + cj * (int)S) * FCHUNK + (tid & 255);
         const int pc = min(p, p_last);                           // a lane past the end repeats the last prior (its keys are ignored)
-        const float4 pb = point_form(a.priors[pc]);
+        const float4 pb = point_form(cur);
         const float area_b = box_area(pb);
         float best = 0.f;                                        // IoU >= 0: row 0 wins an all-zero column
         int bidx = 0;
@@ -365,39 +405,19 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(FusedArgs a) {
         npos = warp_sum(npos);
         if (lane == 0) s_wi[warp] = npos;
         __syncthreads();
-        if (tid == 0) {
-            int tot = 0;
-            for (int w = 0; w < NW; ++w) tot += s_wi[w];
-            s_npos_cta = tot;
-            if (S == 1) s_npos_img = tot;
-            atomicAdd(&a.state->n_pos, tot);
-            __threadfence();
-            const unsigned old = atomicAdd(&a.state->bar2, 1u);
-            if (old == n_ctas - 1 && a.x.world > 0) {
-                const unsigned long long word = ((unsigned long long)epoch << 32) | (unsigned)atomicAdd(&a.state->n_pos, 0);
-                for (int r = 0; r < a.x.world; ++r)
-                    *reinterpret_cast<volatile unsigned long long *>(&a.x.peers[r]->npos[epoch & 1][a.x.rank]) = word;
-                __threadfence_system();
+        if (warp == 0) {
+            const int tot = warp_sum(lane < NW ? s_wi[lane] : 0);
+            if (lane == 0) {
+                s_npos_cta = tot;
+                if (S == 1) s_npos_img = tot;
+                publish(1, (uint32_t)tot);
             }
         }
     }
     GSSD_PHASE(fused, 3, dbg);
 
     // ---- D. the batch max of conf, then the mining keys (multibox_loss.py:91-99) ---------------------------------------------
-    if (warp == 0) {
-        uint32_t mo = 0;
-        if (a.x.world > 0) {
-            if (lane < a.x.world)
-                mo = (uint32_t)xchg_wait(&a.x.peers[a.x.rank]->xmax[epoch & 1][lane], epoch, a.x.timeout_ns);
-#pragma unroll
-            for (int o = 16; o; o >>= 1) mo = max(mo, __shfl_xor_sync(FULL, mo, o));
-        } else if (lane == 0) {
-            bar_wait(&a.state->bar1, n_ctas);
-            mo = ld_acquire_gpu(&a.state->xmax_ord);
-        }
-        if (lane == 0) s_xmax_ord = mo;
-    }
-    __syncthreads();
+    collect(0, &s_xmax_ord);
     const float x_max = ord2f(s_xmax_ord);
     for (int li = tid; li < my_chunks * FCHUNK; li += NT) {
         const int p = ((int)rank + (li >> 8) * (int)S) * FCHUNK + (li & 255);
@@ -434,6 +454,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(FusedArgs a) {
             for (unsigned r = 0; r < S; ++r) atomicAdd(cluster.map_shared_rank(&s_npos_img, r), s_npos_cta);
         cluster.sync();
     }
+    GSSD_PHASE(fused, 8, dbg);
     const int num_pos = s_npos_img;
     long long k_ll = (long long)a.ratio * num_pos;
     if (k_ll > a.P - 1) k_ll = a.P - 1;
@@ -445,7 +466,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(FusedArgs a) {
         int pass = 0;
         while (true) {
             // the bin that holds the k_rem-th largest composite: suffix sums over the bins, a contiguous run of bins per thread
-            const uint32_t *tot = S > 1 ? total + (pass & 1) * FBINS : hist;
+            const uint32_t *tot = hist + (S > 1 ? (1 + (pass & 1)) * FBINS : 0);          // total = hist + FBINS: one shared base
             const int nb = 1 << fpass_bits(pass);
             constexpr int BPT = FBINS / NT > 0 ? FBINS / NT : 1;
             uint32_t mine = 0;
@@ -460,8 +481,9 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(FusedArgs a) {
             }
             if (lane == 0) s_wtot[warp] = incl;
             __syncthreads();
-            uint32_t above = 0;
-            for (int w = warp + 1; w < NW; ++w) above += s_wtot[w];
+            uint32_t above = (lane > warp && lane < NW) ? s_wtot[lane] : 0u;           // composites in the runs of the warps above
+#pragma unroll
+            for (int o = 16; o; o >>= 1) above += __shfl_xor_sync(FULL, above, o);
             uint32_t run = above + incl - mine;                  // composites in bins above this thread's run
             if (tid * BPT < nb && run < k_rem && k_rem <= run + mine) {
 #pragma unroll
@@ -474,6 +496,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(FusedArgs a) {
             __syncthreads();
             prefix = (prefix << fpass_bits(pass)) | s_digit;
             k_rem = s_krem; eq = s_eq;
+            GSSD_PHASE(fused, 9, dbg);
             if (eq <= (uint32_t)FCAND || pass == 4) break;
             ++pass;
             // next digit of the composites that share the prefix
@@ -496,31 +519,44 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(FusedArgs a) {
                 cluster.sync();
             }
         }
-        // the members of the cut bin go to every CTA of the image and are ranked there by counting
+        // the members of the cut bin: compacted locally (shared-memory atomics), then copied into this CTA's region of every
+        // CTA of the image with plain stores — a remote atomic that returns a slot costs a round trip per candidate
         const int sh = fpass_shift(pass);
+        unsigned long long *mine = cand + (size_t)rank * FCAND;
         for (int li = tid; li < my_chunks * FCHUNK; li += NT) {
             const int p = ((int)rank + (li >> 8) * (int)S) * FCHUNK + (li & 255);
             if (p >= a.P) continue;
             const unsigned long long c = fcomp(keys[li], p);
-            if ((c >> sh) == prefix) {
-                if (S > 1) {
-                    for (unsigned r = 0; r < S; ++r) {
-                        const uint32_t slot = atomicAdd(cluster.map_shared_rank(&s_cand_count, r), 1u);
-                        cluster.map_shared_rank(cand, r)[slot] = c;
-                    }
-                } else {
-                    cand[atomicAdd(&s_cand_count, 1u)] = c;
-                }
-            }
+            if ((c >> sh) == prefix) mine[atomicAdd(&s_cand_count, 1u)] = c;
         }
-        if (S > 1) cluster.sync(); else __syncthreads();
+        __syncthreads();
+        GSSD_PHASE(fused, 10, dbg);
+        const uint32_t n_mine = s_cand_count;
+        if (S > 1) {
+            for (unsigned i = tid; i < n_mine * S; i += NT) {
+                const unsigned r = i / n_mine, j = i - r * n_mine;
+                if (r != rank) cluster.map_shared_rank(cand, r)[(size_t)rank * FCAND + j] = mine[j];
+            }
+            if (tid < S && tid != rank) cluster.map_shared_rank(s_cand_n, tid)[rank] = n_mine;
+            if (tid == 0) s_cand_n[rank] = n_mine;
+            cluster.sync();
+            // flatten: region r holds s_cand_n[r] composites; eq of them in total
+            if (tid < (int)eq) {
+                int r = 0, j = tid;
+                while (j >= (int)s_cand_n[r]) { j -= (int)s_cand_n[r]; ++r; }
+                flat[tid] = cand[(size_t)r * FCAND + j];
+            }
+            __syncthreads();
+        }
+        GSSD_PHASE(fused, 11, dbg);
+        const unsigned long long *list = cand + (S > 1 ? (size_t)S * FCAND : (size_t)rank * FCAND);   // flat or mine: one shared base
         {
-            constexpr int R = NT / FCAND;                        // threads per candidate
+            int R = 1;                                           // threads per candidate: as many as the CTA has to spare
+            while (R < 32 && 2 * R * (int)eq <= NT) R <<= 1;
             const int ci = tid / R, part = tid % R;
-            const unsigned long long c = ci < (int)eq ? cand[ci] : 0ull;
+            const unsigned long long c = ci < (int)eq ? list[ci] : 0ull;
             uint32_t cnt = 0;
-            for (int j = part; j < (int)eq; j += R) cnt += cand[j] > c;
-#pragma unroll
+            for (int j = part; j < (int)eq; j += R) cnt += list[j] > c;
             for (int o = R >> 1; o; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
             if (ci < (int)eq && part == 0 && cnt == k_rem - 1) s_cut = c;
         }
@@ -530,20 +566,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(FusedArgs a) {
     GSSD_PHASE(fused, 5, dbg);
 
     // ---- F. N, then smooth-L1 (80-88), cross-entropy over pos | neg (108-113) and every gradient ----------------------------------------
-    if (warp == 0) {
-        int nt = 0;
-        if (a.x.world > 0) {
-            if (lane < a.x.world)
-                nt = (int)(uint32_t)xchg_wait(&a.x.peers[a.x.rank]->npos[epoch & 1][lane], epoch, a.x.timeout_ns);
-#pragma unroll
-            for (int o = 16; o; o >>= 1) nt += __shfl_xor_sync(FULL, nt, o);
-        } else if (lane == 0) {
-            bar_wait(&a.state->bar2, n_ctas);
-            nt = (int)ld_acquire_gpu(reinterpret_cast<const uint32_t *>(&a.state->n_pos));
-        }
-        if (lane == 0) s_ntotal = nt;
-    }
-    __syncthreads();
+    collect(1, reinterpret_cast<uint32_t *>(&s_ntotal));
     const int n_total = s_ntotal;
     const float n_f = (float)n_total;
     double acc_l = 0.0, acc_c = 0.0;
@@ -605,25 +628,26 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(FusedArgs a) {
     GSSD_PHASE(fused, 6, dbg);
 
     // ---- G. finish -------------------------------------------------------------------------------------------------------------
+    // Every CTA leaves its two partial sums (reduced in double, rounded once to float) in its own tagged words; CTA 0 of the
+    // grid waits for all of them, adds them in CTA order (deterministic) in double and divides by N.  No fence, no atomic,
+    // and nobody but CTA 0 waits.
     acc_l = warp_sum(acc_l); acc_c = warp_sum(acc_c);
     if (lane == 0) { s_red[0][warp] = acc_l; s_red[1][warp] = acc_c; }
     __syncthreads();
-    const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
     if (tid == 0) {
         double l = 0.0, c = 0.0;
         for (int w = 0; w < NW; ++w) { l += s_red[0][w]; c += s_red[1][w]; }
-        a.partials[2 * cta] = l; a.partials[2 * cta + 1] = c;
-        __threadfence();
-        s_last = atomicAdd(&a.state->done, 1u) == n_ctas - 1;
+        *reinterpret_cast<volatile unsigned long long *>(&a.state->slot[2][cta]) = ((unsigned long long)epoch << 32) | __float_as_uint((float)l);
+        *reinterpret_cast<volatile unsigned long long *>(&a.state->slot[3][cta]) = ((unsigned long long)epoch << 32) | __float_as_uint((float)c);
     }
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
+    if (cta == 0) {
         double l = 0.0, c = 0.0;
-        for (unsigned i = tid; i < n_ctas; i += NT) {            // fixed order -> deterministic
-            l += __ldcg(&a.partials[2 * i]); c += __ldcg(&a.partials[2 * i + 1]);
+        for (unsigned i = tid; i < n_ctas; i += NT) {
+            l += (double)__uint_as_float(slot_wait(&a.state->slot[2][i], epoch, 4000000000ull));
+            c += (double)__uint_as_float(slot_wait(&a.state->slot[3][i], epoch, 4000000000ull));
         }
         l = warp_sum(l); c = warp_sum(c);
+        __syncthreads();
         if (lane == 0) { s_red[0][warp] = l; s_red[1][warp] = c; }
         __syncthreads();
         if (tid == 0) {
@@ -631,9 +655,9 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(FusedArgs a) {
             for (int w = 0; w < NW; ++w) { l += s_red[0][w]; c += s_red[1][w]; }
             a.losses[0] = __fdiv_rn((float)l, n_f);              // multibox_loss.py:117-119
             a.losses[1] = __fdiv_rn((float)c, n_f);
-            // everybody has left: the rendezvous counters are ready for the next launch on this state
-            a.state->bar1 = 0; a.state->bar2 = 0; a.state->xmax_ord = 0; a.state->n_pos = 0; a.state->done = 0;
-            if (a.x.world > 0) *reinterpret_cast<volatile uint32_t *>(&a.x.peers[a.x.rank]->epoch) = epoch;
+            // every CTA has published its last word: the next launch on this state is a new epoch
+            if (multi) *reinterpret_cast<volatile uint32_t *>(&a.x.peers[a.x.rank]->epoch) = epoch;
+            else *reinterpret_cast<volatile uint32_t *>(&a.state->epoch) = epoch;
         }
     }
     GSSD_PHASE(fused, 7, dbg);
@@ -642,7 +666,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(FusedArgs a) {
 static size_t fused_smem_bytes(int g_max, int S, int items, int C) {
     const size_t Gp = (size_t)((g_max + 1) & ~1);
     size_t b = Gp * 8 + (S > 1 ? (size_t)S * Gp * 8 : 0) + (size_t)g_max * (16 + 4 + 4 + 4 + 4) + 16;
-    b += (size_t)3 * FBINS * 4 + (size_t)FCAND * 8;
+    b += (size_t)3 * FBINS * 4 + (size_t)(S + 1) * FCAND * 8;
     b += (size_t)items * (4 + 4 * (size_t)C + 2) + 16;
     return b;
 }
@@ -713,7 +737,7 @@ static FusedPlan fused_plan_uncached(int B, int P, int C, int g_max, const void 
         cfg.attrs = attr; cfg.numAttrs = 1;
         int clusters = 0;
         if (cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
-        if (clusters < B) continue;
+        if (clusters < B || (long)B * S > GSSD_FUSED_MAX_CTAS) continue;
         pl.S = S; pl.NT = NT; pl.items = items; pl.smem = smem;
         *kern_out = kern;
         return pl;
@@ -751,7 +775,7 @@ extern "C" int gssd_mbox_loss_fused(const float *loc, const float *conf, const f
     const void *kern = nullptr;
     const FusedPlan pl = fused_plan(B, P, C, g_max, &kern, c2, gr);
     if (pl.S == 0) return GSSD_ERR_UNSUPPORTED;
-    if (pl.smem < fused_smem_bytes(g_max, pl.S, pl.items, C)) return GSSD_ERR_UNSUPPORTED;
+    if (pl.smem < fused_smem_bytes(g_max, pl.S, pl.items, C) || (long)B * pl.S > GSSD_FUSED_MAX_CTAS) return GSSD_ERR_UNSUPPORTED;
     FusedArgs a = {};
     a.loc = reinterpret_cast<const float4 *>(loc); a.conf = conf; a.priors = reinterpret_cast<const float4 *>(priors);
     a.B = B; a.P = P; a.C = C; a.gt = gt; a.gt_off = gt_off;
@@ -774,7 +798,7 @@ extern "C" int gssd_mbox_loss_fused(const float *loc, const float *conf, const f
     attr[1].val.cooperative = 1;
     cfg.attrs = attr;
     void *params[] = {&a};
-    static int coop_ok = 1;                                      // cluster + cooperative in one launch: dropped if the runtime refuses
+    static int coop_ok = []{ const char *e = getenv("GSSD_FUSED_COOP"); return e && atoi(e) == 0 ? 0 : 1; }();   // cluster + cooperative in one launch: dropped if the runtime refuses
     if (coop_ok) {
         cfg.numAttrs = 2;
         cudaError_t e = cudaLaunchKernelExC(&cfg, kern, params);

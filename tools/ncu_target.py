@@ -28,7 +28,12 @@ ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
 out = torch.empty(B, 2, 200, 5, device=dev)
 bias = (ctypes.c_float * 2)(0.0, -4.0)
 st = _lib.stream()
+state = torch.zeros(int(lib.gssd_fused_state_bytes()), dtype=torch.uint8, device=dev)
+npos = torch.empty(B, dtype=torch.int32, device=dev)
+fused_ok = lib.gssd_mbox_fused_supported(B, P, 2, g_max) == 1
 for _ in range(reps):
+    if fused_ok:
+        _lib.check(lib.gssd_mbox_loss_fused(loc.data_ptr(), conf.data_ptr(), pri.data_ptr(), B, P, 2, gt.data_ptr(), gt_off.data_ptr(), sum_g, g_max, 0.5, 3, 0.1, 0.2, state.data_ptr(), None, losses.data_ptr(), gl.data_ptr(), gc.data_ptr(), None, None, npos.data_ptr(), ws.data_ptr(), wsb, st))
     _lib.check(lib.gssd_mbox_match(pri.data_ptr(), P, conf.data_ptr(), 2, gt.data_ptr(), gt_off.data_ptr(), B, sum_g, g_max, 0.5, tags.data_ptr(), stats.data_ptr(), st))
     _lib.check(lib.gssd_mbox_loss(loc.data_ptr(), conf.data_ptr(), pri.data_ptr(), B, P, 2, gt.data_ptr(), gt_off.data_ptr(), sum_g, g_max, tags.data_ptr(), stats.data_ptr(), None, 0, 3, 0.1, 0.2, losses.data_ptr(), gl.data_ptr(), gc.data_ptr(), None, None, ws.data_ptr(), wsb, st))
     _lib.check(lib.gssd_detect_logits(loc.data_ptr(), conf.data_ptr(), bias, pri.data_ptr(), B, P, 2, 200, 0.2, 0.45, 0.1, 0.2, out.data_ptr(), None, None, st))

@@ -11,7 +11,8 @@ import runpy
 for args in (["32", "v2", "5", "2"], ["256", "v2", "5", "2"], ["1024", "v2", "5", "2"], ["64", "v2_512", "32", "2"]):
     sys.argv = ["ncu_target.py"] + args
     runpy.run_path(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_target.py"), run_name="__main__")
-    for name, labels in (("match", ["sweep", "reduce+force", "emit", "tail-sync"]),
+    for name, labels in (("fused", ["conf->smem+max", "IoU sweep", "exchange+force+count", "wait xmax+keys", "select", "wait N+sweep2", "finish"]),
+                         ("match", ["sweep", "reduce+force", "emit", "tail-sync"]),
                          ("loss", ["sweep1", "select", "sweep2", "finish"]),
                          ("detect", ["threshold", "select", "collect", "sort", "decode", "mask", "resolve", "emit"])):
         buf = (ctypes.c_longlong * 32)()
@@ -20,6 +21,9 @@ for args in (["32", "v2", "5", "2"], ["256", "v2", "5", "2"], ["1024", "v2", "5"
         d = [t[i + 1] - t[i] for i in range(len(labels))]
         print("B=%s %s %-7s total %7d cyc: " % (args[0], args[1], name, t[len(labels)] - t[0]) +
               "  ".join("%s=%d" % (l, x) for l, x in zip(labels, d)), flush=True)
+        if name == "fused":
+            print("      A: issue+GT=%d cp.async wait+sync=%d cluster_arrive=%d max+publish=%d | select: exchange1=%d scan=%d local gather=%d copy+sync+flatten=%d rank=%d" % (
+                t[12] - t[0], t[13] - t[12], t[14] - t[13], t[1] - t[14], t[8] - t[4], t[9] - t[8], t[10] - t[9], t[11] - t[10], t[5] - t[11]), flush=True)
         if name == "loss":     # stamps inside the select: [zeroed, counted, pushed+barrier, suffix] per pass, then [gathered+barrier, ranked]
             sel = [x for x in t[8:24] if x > 0]
             print("      select stamps (cycles after sweep 1): " + " ".join(str(x - t[1]) for x in sel), flush=True)

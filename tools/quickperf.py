@@ -57,7 +57,7 @@ def run(pname, B, gmax):
     def k_loss(i):
         _lib.check(lib.gssd_mbox_loss(locs[i].data_ptr(), confs[i].data_ptr(), pri.data_ptr(), B, P, 2, gt.data_ptr(), gt_off.data_ptr(), sum_g, g_max, tags.data_ptr(), stats.data_ptr(), None, 0, 3, 0.1, 0.2, losses.data_ptr(), gl[i].data_ptr(), gc[i].data_ptr(), None, None, ws.data_ptr(), wsb, st))
 
-    state = torch.zeros(64, dtype=torch.uint8, device=dev)
+    state = torch.zeros(int(lib.gssd_fused_state_bytes()), dtype=torch.uint8, device=dev)
     npos = torch.empty(B, dtype=torch.int32, device=dev)
     fused_ok = lib.gssd_mbox_fused_supported(B, P, 2, g_max) == 1
 
