@@ -115,6 +115,11 @@ _SIGS = {
     "gssd_nchw_to_pm": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "gssd_pm_to_nchw": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "gssd_maxpool_pm": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
+    "gssd_conv_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "gssd_conv_wgrad_bytes": (_SZ, [_I, _I, _I, _I]),
+    "gssd_head_grad_pm": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "gssd_bn_relu_bwd_pm": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _P, _F, _P, _F, _P, _P, _P]),
+    "gssd_bn_act_pm_to": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _I, _P, _P, _P]),
     "gssd_bn_act_pm": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _F, _I, _P, _P, _P]),
 }
 

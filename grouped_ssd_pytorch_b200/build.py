@@ -11,8 +11,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgssd_b200.so")
-SOURCES = ["abi.cu", "boxes.cu", "match.cu", "loss.cu", "fused.cu", "detect.cu", "gconv.cu", "pipe.cu"]
-HEADERS = ["common.cuh", "select.cuh", "tc.cuh", os.path.join("..", "..", "include", "gssd.h")]
+SOURCES = ["abi.cu", "boxes.cu", "match.cu", "loss.cu", "fused.cu", "detect.cu", "gconv.cu", "gconv_bwd.cu", "pipe.cu"]
+HEADERS = ["common.cuh", "select.cuh", "tc.cuh", "tmap.cuh", os.path.join("..", "..", "include", "gssd.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "-cudart", "static",
 ]
 # gconv.cu is the bf16 tensor-core path (1e-2 tolerance): no bit-exact contract, FMA contraction allowed
-PER_SOURCE_FLAGS = {"gconv.cu": ["-fmad=true"]}
+PER_SOURCE_FLAGS = {"gconv.cu": ["-fmad=true"], "gconv_bwd.cu": ["-fmad=true"]}
 
 
 def _nvcc():

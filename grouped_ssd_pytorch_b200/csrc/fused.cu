@@ -92,8 +92,11 @@ __device__ __forceinline__ uint32_t slot_wait(const unsigned long long *slot, ui
     return (uint32_t)v;
 }
 
+// Registers are held to 64 per thread (two CTAs of 512 threads per SM): Detect runs beside the loss on a second stream with
+// CTAs that fill an SM's register file, so the loss must be able to pack two CTAs onto each of the SMs Detect leaves free —
+// otherwise the cooperative launch waits for Detect to finish and the two kernels serialise.
 template <int NT, bool C2, bool GRADS>
-__global__ void __launch_bounds__(NT, 1) fused_kernel(FusedArgs a) {
+__global__ void __launch_bounds__(NT, NT <= 512 ? 1024 / NT : 1) fused_kernel(FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned S = cluster.num_blocks();
@@ -715,32 +718,37 @@ static FusedPlan fused_plan_uncached(int B, int P, int C, int g_max, const void 
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const int n_chunks = ceil_div(P, FCHUNK);
     const int NT = (forced_nt == 256 || forced_nt == 512 || forced_nt == 1024) ? forced_nt : 512;
-    for (int S = 8; S >= 1; S >>= 1) {
-        if (forced_s && S != forced_s) continue;
-        if (S > 1 && S > n_chunks) continue;
-        const int items = ceil_div(n_chunks, S) * FCHUNK;
-        const size_t smem = fused_smem_bytes(g_max, S, items, C);
-        if (smem > (size_t)optin - 2048) continue;
-        // one CTA per SM keeps every phase at full speed; beyond that only what the occupancy calculator admits
-        if (!forced_s && (long)B * S > sms) {
-            if (S > 1) continue;
+    // first choice: one CTA per SM (every phase at full speed), the widest cluster that allows it; second: two CTAs per SM;
+    // last: whatever the occupancy calculator admits with one CTA per image
+    for (int round = 0; round < 3; ++round) {
+        for (int S = 8; S >= 1; S >>= 1) {
+            if (forced_s && S != forced_s) continue;
+            if (S > 1 && S > n_chunks) continue;
+            if (!forced_s) {
+                if (round == 0 && (long)B * S > sms) continue;
+                if (round == 1 && (long)B * S > 2l * sms) continue;
+                if (round == 2 && S > 1) continue;
+            }
+            const int items = ceil_div(n_chunks, S) * FCHUNK;
+            const size_t smem = fused_smem_bytes(g_max, S, items, C);
+            if (smem > (size_t)optin - 2048) continue;
+            const void *kern = fused_pick(NT, c2, gr);
+            if (allow_max_smem(kern) != cudaSuccess) { cudaGetLastError(); continue; }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(S, B, 1);
+            cfg.blockDim = dim3(NT, 1, 1);
+            cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            int clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
+            if (clusters < B || (long)B * S > GSSD_FUSED_MAX_CTAS) continue;
+            pl.S = S; pl.NT = NT; pl.items = items; pl.smem = smem;
+            *kern_out = kern;
+            return pl;
         }
-        const void *kern = fused_pick(NT, c2, gr);
-        if (allow_max_smem(kern) != cudaSuccess) { cudaGetLastError(); continue; }
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(S, B, 1);
-        cfg.blockDim = dim3(NT, 1, 1);
-        cfg.dynamicSmemBytes = smem;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        int clusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
-        if (clusters < B || (long)B * S > GSSD_FUSED_MAX_CTAS) continue;
-        pl.S = S; pl.NT = NT; pl.items = items; pl.smem = smem;
-        *kern_out = kern;
-        return pl;
     }
     return pl;
 }

@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "tc.cuh"
+#include "tmap.cuh"
 
 namespace gssd {
 
@@ -400,35 +401,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn == nullptr) {
-        void *sym = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(sym);
-    }
-    return fn;
-}
-
 // bf16 matrix [rows, cols] (cols innermost), box = box_rows x 64 columns, 128-byte swizzle, zero fill outside
 static int make_map_2d(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols = 64) {
-    EncodeTiledFn enc = encode_tiled_fn();
-    if (enc == nullptr) return (int)cudaErrorNotSupported;
-    cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {cols * 2};
-    cuuint32_t box[2] = {box_cols, box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+    return make_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, box_rows, box_cols,
+                        box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 template <int BN, int MSUB>
@@ -510,7 +486,7 @@ __global__ void __launch_bounds__(256) pm_to_nchw_kernel(const __nv_bfloat16 *__
 }
 
 // train-mode BN (+ReLU) in place on a PM tensor; one warp per pixel row of c channels
-__global__ void __launch_bounds__(256) bn_act_pm_kernel(__nv_bfloat16 *__restrict__ y, int rows, int c, int hp, int wp, int h, int w,
+__global__ void __launch_bounds__(256) bn_act_pm_kernel(__nv_bfloat16 *y, __nv_bfloat16 *y_out, int rows, int c, int hp, int wp, int h, int w,
                                                         const float *__restrict__ chan_sum, const float *__restrict__ gamma,
                                                         const float *__restrict__ beta, float bn_eps, float inv_count, int relu,
                                                         float *__restrict__ row_ss_out) {
@@ -528,8 +504,13 @@ __global__ void __launch_bounds__(256) bn_act_pm_kernel(__nv_bfloat16 *__restric
         const int rem = m % (hp * wp), py = rem / wp, px = rem - py * wp;
         const bool interior = py >= 1 && py <= h && px >= 1 && px <= w;
         float ss = 0.f;
+        if (!interior && y_out != y) {                                       // out of place: the border of the output is zero too
+            uint4 *orow = reinterpret_cast<uint4 *>(y_out + (size_t)m * c);
+            for (int i = lane; i < c / 8; i += 32) orow[i] = make_uint4(0, 0, 0, 0);
+        }
         if (interior) {
-            uint4 *row = reinterpret_cast<uint4 *>(y + (size_t)m * c);
+            const uint4 *row = reinterpret_cast<const uint4 *>(y + (size_t)m * c);
+            uint4 *orow = reinterpret_cast<uint4 *>(y_out + (size_t)m * c);
             for (int i = lane; i < c / 8; i += 32) {
                 uint4 q = row[i];
                 uint32_t *qw = reinterpret_cast<uint32_t *>(&q);
@@ -546,7 +527,7 @@ __global__ void __launch_bounds__(256) bn_act_pm_kernel(__nv_bfloat16 *__restric
                     ss += lo * lo + hi * hi;
                     qw[j] = packed;
                 }
-                row[i] = q;
+                orow[i] = q;
             }
         }
         if (row_ss_out != nullptr) {
@@ -735,8 +716,8 @@ extern "C" int gssd_pm_to_nchw(const void *x_bf16, int n_img, int c, int h, int 
     return GSSD_OK;
 }
 
-extern "C" int gssd_bn_act_pm(void *y_bf16, int n_img, int c, int h, int w, const float *chan_sum, const float *gamma,
-                              const float *beta, float bn_eps, int relu, float *row_ss_out, float *mean_var_out, void *stream) {
+static int bn_act_pm_impl(void *y_bf16, void *y_out_bf16, int n_img, int c, int h, int w, const float *chan_sum, const float *gamma,
+                          const float *beta, float bn_eps, int relu, float *row_ss_out, float *mean_var_out, void *stream) {
     if (y_bf16 == nullptr || chan_sum == nullptr || n_img <= 0 || c <= 0 || h <= 0 || w <= 0) return GSSD_ERR_ARG;
     if (c % 8 || c > 8192) return GSSD_ERR_LIMIT;
     const long rows = (long)n_img * (h + 2) * (w + 2);
@@ -746,7 +727,7 @@ extern "C" int gssd_bn_act_pm(void *y_bf16, int n_img, int c, int h, int w, cons
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int blocks = (int)((rows + 7) / 8 < (long)sms * 8 ? (rows + 7) / 8 : (long)sms * 8);
     bn_act_pm_kernel<<<blocks, 256, 2 * c * sizeof(float), (cudaStream_t)stream>>>(
-        reinterpret_cast<__nv_bfloat16 *>(y_bf16), (int)rows, c, h + 2, w + 2, h, w, chan_sum, gamma, beta, bn_eps,
+        reinterpret_cast<__nv_bfloat16 *>(y_bf16), reinterpret_cast<__nv_bfloat16 *>(y_out_bf16 ? y_out_bf16 : y_bf16), (int)rows, c, h + 2, w + 2, h, w, chan_sum, gamma, beta, bn_eps,
         (float)(1.0 / count), relu, row_ss_out);
     GSSD_AFTER_LAUNCH();
     if (mean_var_out != nullptr) {
@@ -755,6 +736,19 @@ extern "C" int gssd_bn_act_pm(void *y_bf16, int n_img, int c, int h, int w, cons
         GSSD_AFTER_LAUNCH();
     }
     return GSSD_OK;
+}
+
+extern "C" int gssd_bn_act_pm(void *y_bf16, int n_img, int c, int h, int w, const float *chan_sum, const float *gamma,
+                              const float *beta, float bn_eps, int relu, float *row_ss_out, float *mean_var_out, void *stream) {
+    return bn_act_pm_impl(y_bf16, nullptr, n_img, c, h, w, chan_sum, gamma, beta, bn_eps, relu, row_ss_out, mean_var_out, stream);
+}
+
+extern "C" int gssd_bn_act_pm_to(const void *y_bf16, void *y_out_bf16, int n_img, int c, int h, int w, const float *chan_sum,
+                                 const float *gamma, const float *beta, float bn_eps, int relu, float *row_ss_out,
+                                 float *mean_var_out, void *stream) {
+    if (y_out_bf16 == nullptr) return GSSD_ERR_ARG;
+    return bn_act_pm_impl(const_cast<void *>(y_bf16), y_out_bf16, n_img, c, h, w, chan_sum, gamma, beta, bn_eps, relu, row_ss_out,
+                          mean_var_out, stream);
 }
 
 extern "C" int gssd_maxpool_pm(const void *x_bf16, int n_img, int c, int h, int w, int kernel, int stride, int pad, int ceil_mode,

@@ -9,7 +9,10 @@ not own parameters: it is built FROM the reference's own modules (`net.vgg[30]`,
 `net.L2Norm`, `net.fuse_11`, `net.bn_fuse_11`, `net.loc[0]`, `net.conf[0]` ...), so state-dict names and
 checkpoints are the reference's.  Weights are re-packed to bf16 whenever a parameter changes.
 
-Forward only (inference and the forward half of a training step; the backward is SURVEY §8f rank 1).
+With autograd enabled the chain is a `torch.autograd.Function` (`SourceBlock.forward_autograd`): the backward — data gradients on
+the same implicit-GEMM kernel with re-packed filters, weight gradients on the split-K tcgen05 kernel `gssd_conv_wgrad`, BatchNorm
+(batch statistics) / ReLU / L2Norm backward as row kernels on the PM layout — returns what autograd returns through the
+reference's modules, so `gssd_forward` trains.
 No CPU fallback: without a CUDA device every call raises.
 """
 import ctypes as C
@@ -257,17 +260,23 @@ class SourceBlock(object):
         return self._packed
 
     @staticmethod
-    def _bn_train(y, bn, stats, want_ss):
-        """batch-statistics BatchNorm + ReLU in place on the raw conv output; running stats as nn.BatchNorm2d"""
+    def _bn_train(y, bn, stats, want_ss, out=None):
+        """batch-statistics BatchNorm + ReLU on the raw conv output, in place or into `out` (the backward keeps the raw
+        output); running stats as nn.BatchNorm2d"""
         lib = _lib.load()
         dev = y.data.device
         ss = torch.empty((y.rows,), dtype=torch.float32, device=dev) if want_ss else None
         mv = torch.empty((2 * y.c,), dtype=torch.float32, device=dev) if bn.track_running_stats else None
+        gam = _lib.f32(bn.weight, dev) if bn.affine else None
+        bet = _lib.f32(bn.bias, dev) if bn.affine else None
         with torch.cuda.device(dev):
-            _lib.check(lib.gssd_bn_act_pm(y.data.data_ptr(), y.n, y.c, y.h, y.w, stats.data_ptr(),
-                                          _lib.ptr(_lib.f32(bn.weight, dev)) if bn.affine else None,
-                                          _lib.ptr(_lib.f32(bn.bias, dev)) if bn.affine else None,
-                                          float(bn.eps), 1, _lib.ptr(ss), _lib.ptr(mv), _lib.stream()), "gssd_bn_act_pm")
+            if out is None:
+                _lib.check(lib.gssd_bn_act_pm(y.data.data_ptr(), y.n, y.c, y.h, y.w, stats.data_ptr(), _lib.ptr(gam), _lib.ptr(bet),
+                                              float(bn.eps), 1, _lib.ptr(ss), _lib.ptr(mv), _lib.stream()), "gssd_bn_act_pm")
+            else:
+                _lib.check(lib.gssd_bn_act_pm_to(y.data.data_ptr(), out.data.data_ptr(), y.n, y.c, y.h, y.w, stats.data_ptr(),
+                                                 _lib.ptr(gam), _lib.ptr(bet), float(bn.eps), 1, _lib.ptr(ss), _lib.ptr(mv),
+                                                 _lib.stream()), "gssd_bn_act_pm_to")
         if mv is not None:
             with torch.no_grad():
                 bn.num_batches_tracked += 1
@@ -275,6 +284,36 @@ class SourceBlock(object):
                 bn.running_mean.mul_(1 - mom).add_(mv[:y.c].to(bn.running_mean.device), alpha=mom)
                 bn.running_var.mul_(1 - mom).add_(mv[y.c:].to(bn.running_var.device), alpha=mom)
         return ss
+
+    def param_list(self):
+        """(name, tensor or None) of every parameter of the chain, in the order _SourceChainFn takes them"""
+        def wb(m, n):
+            return [(n + "_w", m.weight if m is not None else None), (n + "_b", m.bias if m is not None else None)]
+        return (wb(self.gconv, "gconv") + wb(self.bn if (self.bn is not None and self.bn.affine) else None, "bn") +
+                [("l2norm_w", self.l2norm.weight if self.l2norm is not None else None)] + wb(self.fuse, "fuse") +
+                wb(self.bn_fuse if (self.bn_fuse is not None and self.bn_fuse.affine) else None, "bn_fuse") +
+                wb(self.loc, "loc") + wb(self.conf, "conf"))
+
+    def _pack_dgrad(self, dev):
+        """the three data-gradient convolutions (heads, fuse, grouped conv), re-packed whenever a parameter changes"""
+        mods = (self.gconv, self.l2norm, self.fuse, self.loc, self.conf)
+        key = (_versions(*mods), str(dev))
+        if getattr(self, "_dg_key", None) != key:
+            with torch.no_grad(), torch.cuda.device(dev):
+                wh = torch.cat([_lib.f32(self.loc.weight, dev), _lib.f32(self.conf.weight, dev)], 0)
+                d = dict(h=_DgradConv(wh, 1, dev, pad_in=64),
+                         f=_DgradConv(self.fuse.weight, 1, dev, in_scale=self.l2norm.weight if self.l2norm is not None else None))
+                if self.gconv is not None:
+                    d["g"] = _DgradConv(self.gconv.weight, self.gconv.groups, dev)
+            self._dg, self._dg_key = d, key
+        return self._dg
+
+    def forward_autograd(self, x):
+        """the chain as one autograd node: x NCHW fp32 -> (loc_k[B, n_k, 4], conf_k[B, n_k, C], x_out NCHW or None).  BatchNorm
+        in training mode (batch statistics), in eval mode (running statistics, folded into the conv epilogue) or absent."""
+        prm = [t for _, t in self.param_list()]
+        out = _SourceChainFn.apply(self, x, *prm)
+        return (out[0], out[1], out[2] if len(out) > 2 else None)
 
     def forward(self, x, loc_out, conf_out, prior_off):
         """x: NCHW fp32 tensor or PM.  Writes this source's slice of loc_out[B,P,4] / conf_out[B,P,C] (fp32, CUDA) at
@@ -312,6 +351,180 @@ class SourceBlock(object):
     __call__ = forward
 
 
+
+# ---- the chain under autograd -------------------------------------------------------------------------------------
+def _wgrad(dy, x, c_out, groups, taps):
+    """weight gradient of a stride-1 'same' convolution: dy PM [rows, >= c_out], x PM [rows, c_in] -> fp32 [c_out, c_in/groups, k, k]"""
+    lib = _lib.load()
+    dev = x.data.device
+    cg = x.c // groups
+    nbytes = lib.gssd_conv_wgrad_bytes(x.c, c_out, groups, taps)
+    dw = torch.empty((nbytes // 4,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.gssd_conv_wgrad(dy.data.data_ptr(), x.data.data_ptr(), x.n, x.h, x.w, x.c, c_out, dy.c, groups, taps,
+                                       dw.data_ptr(), _lib.stream()), "gssd_conv_wgrad")
+    k = 3 if taps == 9 else 1
+    dw = dw.view(taps, -1, cg)[:, :c_out]                                # [taps, c_out, cg]
+    return dw.permute(1, 2, 0).reshape(c_out, cg, k, k)
+
+
+class _DgradConv(object):
+    """the convolution that computes the data gradient of `weight` (see dgrad_weight), packed for gssd_conv_igemm; the input
+    channels (= output channels of the forward conv) are zero-padded to `pad_in` for the heads"""
+
+    def __init__(self, weight, groups, dev, in_scale=None, pad_in=None):
+        import torch.nn as nn
+        w = _lib.f32(weight, dev)
+        if in_scale is not None:                                         # L2Norm.weight folded into the forward filter
+            w = w * _lib.f32(in_scale, dev).view(1, -1, 1, 1)
+        wd = dgrad_weight(w, groups)                                     # [c_in, c_out/groups, k, k]
+        if pad_in is not None and wd.shape[1] < pad_in:
+            wd = torch.cat([wd, wd.new_zeros((wd.shape[0], pad_in - wd.shape[1]) + tuple(wd.shape[2:]))], 1)
+        k = wd.shape[2]
+        conv = nn.Conv2d(wd.shape[1] * groups, wd.shape[0], k, padding=k // 2, groups=groups, bias=False).to(dev)
+        with torch.no_grad():
+            conv.weight.copy_(wd)
+        self.cv = _Conv(conv, groups, dev=dev)
+
+
+def _bn_relu_bwd(dy, y, yraw, add, stats, gamma, bn_eps, ss_l2, l2_eps, ss_out, l2_eps_out, ebn=None):
+    """gssd_bn_relu_bwd_pm -> (dx PM, sums[3c] = (dbeta, dgamma, dbias))"""
+    lib = _lib.load()
+    dev = dy.data.device
+    out = PM.empty(dy.n, dy.c, dy.h, dy.w, dev)
+    sums = torch.empty((3 * dy.c,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.gssd_bn_relu_bwd_pm(dy.data.data_ptr(), y.data.data_ptr(), _lib.ptr(yraw.data if yraw is not None else None),
+                                           _lib.ptr(add.data if add is not None else None), dy.n, dy.c, dy.h, dy.w,
+                                           _lib.ptr(stats), _lib.ptr(gamma), float(bn_eps), 1,
+                                           _lib.ptr(ebn[0] if ebn else None), _lib.ptr(ebn[1] if ebn else None), _lib.ptr(ss_l2), float(l2_eps),
+                                           _lib.ptr(ss_out), float(l2_eps_out), out.data.data_ptr(), sums.data_ptr(), _lib.stream()),
+                   "gssd_bn_relu_bwd_pm")
+    return out, sums
+
+
+class _SourceChainFn(torch.autograd.Function):
+    """One source chain under autograd.  forward(blk, x, *params) -> (loc_k[B, n_k, 4], conf_k[B, n_k, C], x_out NCHW or None);
+    `params` = the tensors of SourceBlock.param_list() (only there so that autograd routes their gradients)."""
+
+    @staticmethod
+    def forward(ctx, blk, x, *params):
+        dev = _lib.device_of(x)
+        with torch.cuda.device(dev):
+            x0 = x if isinstance(x, PM) else PM.from_nchw(x)
+            g, f, h, training = blk._pack(dev)
+            want_l2 = blk.l2norm is not None
+            eps = blk.l2norm.eps if want_l2 else 0.0
+            sv = dict(x0=x0, training=training, l2=want_l2, eps=eps)
+            ss = torch.empty((x0.rows,), dtype=torch.float32, device=dev) if want_l2 else None
+            if g is not None:
+                if training and blk.bn is not None:
+                    stats1 = torch.zeros((2 * g.c_out,), dtype=torch.float32, device=dev)
+                    y1raw = conv_igemm(x0, g, relu=False, shift=g.bias, chan_sum=stats1)
+                    y1 = PM.empty(y1raw.n, y1raw.c, y1raw.h, y1raw.w, dev)
+                    ss = blk._bn_train(y1raw, blk.bn, stats1, want_l2, out=y1)
+                    sv.update(y1raw=y1raw, stats1=stats1)
+                else:
+                    y1 = conv_igemm(x0, g, relu=True, scale=g.scale, shift=g.shift, row_ss_out=ss)
+            else:
+                if want_l2:
+                    raise NotImplementedError("L2Norm without the grouped conv in front")
+                y1 = x0
+            if training and blk.bn_fuse is not None:
+                stats2 = torch.zeros((2 * f.c_out,), dtype=torch.float32, device=dev)
+                y2raw = conv_igemm(y1, f, relu=False, shift=f.bias, chan_sum=stats2, row_ss_in=ss, l2_eps=eps)
+                z2 = PM.empty(y2raw.n, y2raw.c, y2raw.h, y2raw.w, dev)
+                blk._bn_train(y2raw, blk.bn_fuse, stats2, False, out=z2)
+                sv.update(y2raw=y2raw, stats2=stats2)
+            else:
+                z2 = conv_igemm(y1, f, relu=True, scale=f.scale, shift=f.shift, row_ss_in=ss, l2_eps=eps)
+            n_k = x0.h * x0.w * blk.n_anchor
+            loc = torch.empty((x0.n, n_k, 4), dtype=torch.float32, device=dev)
+            conf = torch.empty((x0.n, n_k, blk.num_classes), dtype=torch.float32, device=dev)
+            conv_igemm(z2, h, relu=False, shift=h.bias, head=(loc, conf, blk.n_anchor, blk.num_classes, 0, n_k))
+            sv.update(y1=y1, z2=z2, ss=ss, n_k=n_k)
+            x_out = y1.to_nchw() if g is not None else None
+        ctx.blk, ctx.sv = blk, sv
+        ctx.x_is_pm = isinstance(x, PM)
+        if x_out is None:
+            return loc, conf
+        return loc, conf, x_out
+
+    @staticmethod
+    def backward(ctx, d_loc, d_conf, d_xout=None):
+        blk, sv = ctx.blk, ctx.sv
+        lib = _lib.load()
+        x0, y1, z2, ss = sv["x0"], sv["y1"], sv["z2"], sv["ss"]
+        dev = x0.data.device
+        A, NC = blk.n_anchor, blk.num_classes
+        c_head = A * (4 + NC)
+        training = sv["training"]
+        with torch.no_grad(), torch.cuda.device(dev):
+            g, f, h, _ = blk._pack(dev)
+            dg = blk._pack_dgrad(dev)
+            grads = {}
+            # ---- heads -----------------------------------------------------------------------------------------------------
+            if d_loc is None:
+                d_loc = torch.zeros((x0.n, sv["n_k"], 4), dtype=torch.float32, device=dev)
+            if d_conf is None:
+                d_conf = torch.zeros((x0.n, sv["n_k"], NC), dtype=torch.float32, device=dev)
+            d_loc, d_conf = _lib.f32(d_loc, dev), _lib.f32(d_conf, dev)
+            dH = PM.empty(x0.n, 64, x0.h, x0.w, dev)
+            bias_h = torch.empty((c_head,), dtype=torch.float32, device=dev)
+            _lib.check(lib.gssd_head_grad_pm(d_loc.data_ptr(), d_conf.data_ptr(), x0.n, x0.h, x0.w, sv["n_k"], 0, A, NC, 64,
+                                             dH.data.data_ptr(), bias_h.data_ptr(), _lib.stream()), "gssd_head_grad_pm")
+            dWh = _wgrad(dH, z2, c_head, 1, 9)
+            grads["loc_w"], grads["conf_w"] = dWh[:4 * A], dWh[4 * A:]
+            grads["loc_b"], grads["conf_b"] = bias_h[:4 * A], bias_h[4 * A:]
+            dz2 = conv_igemm(dH, dg["h"].cv, relu=False)
+            # ---- bn_fuse + ReLU (+ the row factor of the deferred L2Norm of the fuse input) ------------------------------
+            bnf = blk.bn_fuse
+            if training and bnf is not None:
+                t2, s2 = _bn_relu_bwd(dz2, z2, sv["y2raw"], None, sv["stats2"], _lib.f32(bnf.weight, dev) if bnf.affine else None,
+                                      bnf.eps, None, 0.0, ss, sv["eps"])
+                grads["bn_fuse_b"], grads["bn_fuse_w"] = s2[:f.c_out], s2[f.c_out:2 * f.c_out]
+            else:
+                ebn = (_lib.f32(bnf.weight, dev), _lib.f32(bnf.bias, dev)) if (bnf is not None and bnf.affine) else None
+                t2, s2 = _bn_relu_bwd(dz2, z2, None, None, None, f.scale, 0.0, None, 0.0, ss, sv["eps"], ebn=ebn)
+                if ebn is not None:
+                    grads["bn_fuse_b"], grads["bn_fuse_w"] = s2[:f.c_out], s2[f.c_out:2 * f.c_out]
+            grads["fuse_b"] = s2[2 * f.c_out:]
+            dWf = _wgrad(t2, y1, f.c_out, 1, 1)                          # w.r.t. the filter as packed (L2Norm.weight folded in)
+            if sv["l2"]:
+                l2w = _lib.f32(blk.l2norm.weight, dev)
+                grads["l2norm_w"] = (dWf * _lib.f32(blk.fuse.weight, dev)).sum(dim=(0, 2, 3))
+                grads["fuse_w"] = dWf * l2w.view(1, -1, 1, 1)
+            else:
+                grads["fuse_w"] = dWf
+            a1 = conv_igemm(t2, dg["f"].cv, relu=False)
+            # ---- bn + ReLU of the grouped conv (+ the L2Norm backward, + what flows back from further down the backbone) ------
+            if g is None:
+                dx = a1
+            else:
+                add = PM.from_nchw(d_xout) if d_xout is not None else None
+                bn = blk.bn
+                if training and bn is not None:
+                    d1, s1 = _bn_relu_bwd(a1, y1, sv["y1raw"], add, sv["stats1"], _lib.f32(bn.weight, dev) if bn.affine else None,
+                                          bn.eps, ss if sv["l2"] else None, sv["eps"], None, 0.0)
+                    grads["bn_b"], grads["bn_w"] = s1[:g.c_out], s1[g.c_out:2 * g.c_out]
+                else:
+                    ebn = (_lib.f32(bn.weight, dev), _lib.f32(bn.bias, dev)) if (bn is not None and bn.affine) else None
+                    d1, s1 = _bn_relu_bwd(a1, y1, None, add, None, g.scale, 0.0, ss if sv["l2"] else None, sv["eps"], None, 0.0, ebn=ebn)
+                    if ebn is not None:
+                        grads["bn_b"], grads["bn_w"] = s1[:g.c_out], s1[g.c_out:2 * g.c_out]
+                grads["gconv_b"] = s1[2 * g.c_out:]
+                grads["gconv_w"] = _wgrad(d1, x0, g.c_out, g.groups, g.taps)
+                dx = conv_igemm(d1, dg["g"].cv, relu=False)
+            gx = dx if ctx.x_is_pm else dx.to_nchw()
+        out = [None, gx if ctx.needs_input_grad[1] else None]
+        for name, prm in blk.param_list():
+            gr = grads.get(name)
+            if gr is not None and prm is not None:
+                gr = gr.reshape(prm.shape).to(prm.dtype)
+            out.append(gr)
+        return tuple(out)
+
+
 # ---- the model's forward with the source blocks swapped in ---------------------------------------------------
 def build_source_blocks(net):
     """SourceBlocks for the six sources of a reference `SSD` (ssd_type gssd: no self-attention, no DCN), built from
@@ -339,8 +552,9 @@ def build_source_blocks(net):
 def gssd_forward(net, x, detect_args=(0, 200, 0.01, 0.45), backbone=False):
     """Forward of the reference's SSD (ssd_multiphase_custom_group.py:217-400, ssd_type gssd) with every source chain
     — grouped conv / BN / ReLU / L2Norm / fuse 1x1 / BN / ReLU / loc+conf heads / permute / flatten / concat — run by
-    the tcgen05 source blocks; the rest of the backbone stays the model's own torch modules.  Forward only
-    (torch.no_grad): returns what `net(x)` returns — `(loc[B,P,4], conf[B,P,C], priors)` in the train phase,
+    the tcgen05 source blocks; the rest of the backbone stays the model's own torch modules.  With autograd enabled the
+    source chains are autograd nodes (their backward runs on the same kernels), so `loss.backward()` reaches every
+    parameter exactly as through the reference forward; returns what `net(x)` returns — `(loc[B,P,4], conf[B,P,C], priors)` in the train phase,
     `Detect` output `[B,C,top_k,5]` in the test phase (ssd_multiphase_custom_group.py:382-396).
 
         net.forward = types.MethodType(gssd_forward, net)        # drop-in
@@ -349,28 +563,44 @@ def gssd_forward(net, x, detect_args=(0, 200, 0.01, 0.45), backbone=False):
     BatchNorm folded, ReLU fused and the pools on the PM layout — in bf16: 1.5x the model's fp32 torch forward at batch 32,
     at 1.0e-2 / 6.6e-3 relative error on loc / conf instead of 6.0e-3 / 3.7e-3 (tests/test_gpu_model.py).
     """
+    import contextlib
     import torch.nn.functional as F
     from ..functions import Detect
     _lib.require_cuda()
-    if net.training and torch.is_grad_enabled() and not getattr(net, "_gssd_warned", False):
-        import warnings
-        warnings.warn("gssd_forward is forward-only: no autograd graph is recorded through the source blocks "
-                      "(train-mode BatchNorm statistics are still updated)")
-        net._gssd_warned = True
     cache = getattr(net, "_gssd_blocks", None)
     if cache is None:
         cache = build_source_blocks(net)
         net._gssd_blocks = cache
     blocks, (i43, i7) = cache
     bn = bool(net.batch_norm)
-    with torch.no_grad():
+    # under autograd every source chain is one autograd node (SourceBlock.forward_autograd) and the layers in between are the
+    # model's own modules, recorded by torch as usual; without it everything runs under no_grad
+    use_ag = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in net.parameters()))
+    with (contextlib.nullcontext() if use_ag else torch.no_grad()):
         x = x.to(_lib.device_of(x))
         B = x.size(0)
         P = net.priors.size(0)
-        loc = torch.empty((B, P, 4), dtype=torch.float32, device=x.device)
-        conf = torch.empty((B, P, net.num_classes), dtype=torch.float32, device=x.device)
         off = 0
-        if backbone and not net.training:
+        if use_ag:
+            locs, confs = [], []
+
+            def run_block(blk, xin):
+                nonlocal off
+                l, c, xo = blk.forward_autograd(xin)
+                locs.append(l); confs.append(c)
+                off += l.shape[1]
+                return xo
+            loc = conf = None
+        else:
+            loc = torch.empty((B, P, 4), dtype=torch.float32, device=x.device)
+            conf = torch.empty((B, P, net.num_classes), dtype=torch.float32, device=x.device)
+
+            def run_block(blk, xin):
+                nonlocal off
+                xo, n = blk(xin, loc, conf, off)
+                off += n
+                return xo
+        if backbone and not net.training and not use_ag:
             # every grouped backbone conv the tcgen05 kernel takes (conv3_2 .. conv5_3) stays in PM/bf16 with BN folded
             run = getattr(net, "_gssd_backbone", None)
             if run is None:
@@ -380,22 +610,18 @@ def gssd_forward(net, x, detect_args=(0, 200, 0.01, 0.45), backbone=False):
             for k in range(first):                               # GSSD:254-259: the layers in front stay torch
                 x = net.vgg[k](x)
             x = run(x, first, i43)
-            x1, n = blocks[0](x, loc, conf, off)                 # conv4_3 .. heads of source 1 (GSSD:258-297, 375-377)
-            off += n
+            x1 = run_block(blocks[0], x)                         # conv4_3 .. heads of source 1 (GSSD:258-297, 375-377)
             x = run(x1, i43 + (3 if bn else 2), i7)              # GSSD:300-301 up to the input of conv7
-            x2, n = blocks[1](x, loc, conf, off)                 # conv7 .. heads of source 2 (GSSD:300-325)
-            off += n
+            x2 = run_block(blocks[1], x)                         # conv7 .. heads of source 2 (GSSD:300-325)
         else:
             for k in range(i43):                                 # GSSD:254-259, up to the input of conv4_3
                 x = net.vgg[k](x)
-            x1, n = blocks[0](x, loc, conf, off)                 # conv4_3 .. heads of source 1 (GSSD:258-297, 375-377)
-            off += n
-            x = x1.to_nchw()                                     # post-ReLU conv4_3 continues down the backbone
+            x1 = run_block(blocks[0], x)                         # conv4_3 .. heads of source 1 (GSSD:258-297, 375-377)
+            x = x1 if use_ag else x1.to_nchw()                   # post-ReLU conv4_3 continues down the backbone
             for k in range(i43 + (3 if bn else 2), i7):          # GSSD:300-301 up to the input of conv7
                 x = net.vgg[k](x)
-            x2, n = blocks[1](x, loc, conf, off)                 # conv7 .. heads of source 2 (GSSD:300-325)
-            off += n
-        x = x2.to_nchw()
+            x2 = run_block(blocks[1], x)                         # conv7 .. heads of source 2 (GSSD:300-325)
+        x = x2 if use_ag else x2.to_nchw()
         si = 2
         for k, v in enumerate(net.extras):                       # GSSD:329-372
             x = v(x)
@@ -407,11 +633,12 @@ def gssd_forward(net, x, detect_args=(0, 200, 0.01, 0.45), backbone=False):
                 x = F.relu(x, inplace=True)
                 is_source = k % 2 == 1
             if is_source:
-                _, n = blocks[si](x, loc, conf, off)
-                off += n
+                run_block(blocks[si], x)
                 si += 1
         if off != P:
             raise RuntimeError("the sources produced %d priors, the model has %d" % (off, P))
+        if use_ag:
+            loc, conf = torch.cat(locs, 1), torch.cat(confs, 1)
         if net.phase == "test":                                  # GSSD:382-390
             return Detect.apply(net.num_classes, detect_args[0], detect_args[1], detect_args[2], detect_args[3],
                                 loc, torch.softmax(conf, dim=-1), net.priors.to(x.device))

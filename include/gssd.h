@@ -320,6 +320,42 @@ GSSD_API int gssd_bn_act_pm(void *y_bf16, int n_img, int c, int h, int w, const 
                    const float *gamma, const float *beta, float bn_eps, int relu,
                    float *row_ss_out, float *mean_var_out, void *stream);
 
+/* the same out of place: y (the raw conv output) stays intact for the backward, the activations go to y_out */
+GSSD_API int gssd_bn_act_pm_to(const void *y_bf16, void *y_out_bf16, int n_img, int c, int h, int w, const float *chan_sum,
+                      const float *gamma, const float *beta, float bn_eps, int relu,
+                      float *row_ss_out, float *mean_var_out, void *stream);
+
+/* ---- backward of the source block (autograd through ssd_multiphase_custom_group.py:258-380) --------------------------
+ * Data gradients need no entry point of their own: the gradient of a stride-1 "same" convolution w.r.t. its input is such
+ * a convolution of dY with the filter rotated by 180 degrees and the channel roles swapped inside each group, i.e.
+ * gssd_conv_igemm on re-packed weights.
+ *
+ * Weight gradient: dw[tap][co][ci] = sum over pixels of dY[pix][co] * X[pix + offset(tap)][ci]  (tcgen05, split over the
+ * pixels, fp32).  dy: PM bf16 [rows, dy_channels] (dy_channels >= c_out, multiple of 64; the columns beyond c_out are
+ * ignored), x: PM bf16 [rows, c_in]; dw: fp32 [taps][c_out_pad][c_in/groups] with c_out_pad = c_out rounded up to 128
+ * (gssd_conv_wgrad_bytes), zeroed and filled by the call.  c_in/groups must be a multiple of 128. */
+GSSD_API int gssd_conv_wgrad(const void *dy_bf16, const void *x_bf16, int n_img, int height, int width, int c_in, int c_out,
+                    int dy_channels, int groups, int taps, float *dw, void *stream);
+GSSD_API size_t gssd_conv_wgrad_bytes(int c_in, int c_out, int groups, int taps);
+/* upstream gradients of one source's slice of loc[B,P,4] / conf[B,P,C] -> PM bf16 [rows, c_pad] with channels
+ * [loc 4A | conf A*C | zeros] (the head's output channels; inverse of the head-mode scatter of gssd_conv_igemm) and their
+ * per-channel sums bias_grad[A*(4+C)] (optional) = the gradients of loc.k.bias / conf.k.bias */
+GSSD_API int gssd_head_grad_pm(const float *d_loc, const float *d_conf, int n_img, int height, int width, int n_priors, int prior_off,
+                      int n_anchor, int n_cls, int c_pad, void *out_bf16, float *bias_grad, void *stream);
+/* ReLU + BatchNorm (batch statistics) backward of one stage on PM tensors, with the L2Norm backward of its consumer folded in:
+ *   g   = dy [- y * (sum_c dy*y) / ((n+eps)*n), n = sqrt(row_ss_l2)]  [+ add]      then  g = 0 where y <= 0 (relu)
+ *   dx  = gamma*rstd*(g - mean(g) - x_hat*mean(g*x_hat))   with chan_sum (the forward's sum / sum of squares; x_hat from yraw)
+ *       = g*gamma                                            without (eval-mode BN folded into gamma, or no BN: gamma NULL)
+ *   out = dx [* 1/(sqrt(row_ss_out)+eps_out)]
+ *   sums[3c] = (sum g = dbeta, sum g*x_hat = dgamma, sum dx = gradient of the conv bias); for an eval-mode BatchNorm that the
+ *   forward folded into the conv epilogue, eval_bn_weight / eval_bn_bias (optional) give dgamma / dbeta with
+ *   x_hat = (y - beta)/gamma taken from the activations (wherever y > 0; elsewhere g = 0) */
+GSSD_API int gssd_bn_relu_bwd_pm(const void *dy_bf16, const void *y_bf16, const void *yraw_bf16, const void *add_bf16, int n_img, int c,
+                        int height, int width, const float *chan_sum, const float *gamma, float bn_eps, int relu,
+                        const float *eval_bn_weight, const float *eval_bn_bias,
+                        const float *row_ss_l2, float l2_eps, const float *row_ss_out, float l2_eps_out,
+                        void *out_bf16, float *sums, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Host-buffer pipeline — the training-step / inference call of the hot path with HOST inputs and outputs:
  * the H2D of train_lesion_multiphase_v2.py:198-200, the criterion call at :246 (MultiBoxLoss forward + the

@@ -175,3 +175,108 @@ def test_train_mode_channel_statistics_at_full_size():
     np.testing.assert_allclose(var.cpu().numpy(), ref.var(dim=(0, 2, 3), unbiased=False).cpu().numpy(), rtol=2e-3, atol=1e-5)
     # against cuDNN's accumulation order a value may round to the neighbouring bf16: one ulp of the top binade = 2^-7 of the max
     assert rel(y.to_nchw().cpu().numpy(), SB.bf16_round(ref.cpu().numpy())) <= 2.0 ** -7
+
+
+# ---- backward of the chain: autograd through SourceBlock.forward_autograd ---------------------------------------------
+def _backward_case(tag):
+    from grouped_ssd_pytorch_b200.layers import SourceBlock
+    x, prm, training = cases.block_case(tag)
+    seed, N, C, H, W, gc, bn, l2, Cf, A, ncls, _ = cases.BLOCK_CASES[tag]
+    mods = modules_from(tag, prm)
+    blk = SourceBlock(*mods, num_classes=ncls)
+    xt = torch.from_numpy(x).cuda().requires_grad_()
+    loc, conf, x_out = blk.forward_autograd(xt)
+    d_loc, d_conf = cases.block_upstream(tag, loc[0].numel(), conf[0].numel())
+    T = lambda a: torch.from_numpy(np.asarray(a, np.float32)).cuda()
+    ((loc.reshape(N, -1) * T(d_loc)).sum() + (conf.reshape(N, -1) * T(d_conf)).sum()).backward()
+    torch.cuda.synchronize()
+    gconv, gbn, l2m, fuse, bn_fuse, locm, confm = mods
+    got = {"x": xt.grad}
+    for name, m in (("gconv", gconv), ("bn", gbn), ("fuse", fuse), ("bn_fuse", bn_fuse), ("loc", locm), ("conf", confm)):
+        if m is not None:
+            got[name + "_w"], got[name + "_b"] = m.weight.grad, m.bias.grad
+    if l2m is not None:
+        got["l2norm_w"] = l2m.weight.grad
+    return {k: v.detach().cpu().numpy() for k, v in got.items()}, (x, prm, training, loc, conf, x_out)
+
+
+@pytest.mark.parametrize("tag", ["s1_train", "s2", "s4", "s1_nobn"])
+def test_source_block_backward_matches_reference_autograd(tag):
+    """every gradient autograd produces on the reference's own modules (tests/golden/source_block_bwd.npz, float64) — input,
+    conv filters and biases, BatchNorm weight / bias in training AND eval mode, L2Norm weight — from the tcgen05 backward: data
+    gradients on the forward kernel, weight gradients on gssd_conv_wgrad, BN / ReLU / L2Norm backward on PM rows.  Tolerance:
+    the north-star 1e-2 of the tensor's scale for the bf16 conv block (five bf16 tensors lie between the loss and the deepest
+    gradient, so the deepest ones are held to 2e-2); the conv bias in front of a training-mode BN has a zero gradient."""
+    g = cases.golden("source_block_bwd")
+    got, (x, prm, training, loc, conf, x_out) = _backward_case(tag)
+    names = sorted(k[len(tag) + 1:-len("_sample")] for k in g.files if k.startswith(tag + "/") and k.endswith("_sample"))
+    assert set(names) == set(got), (names, sorted(got))
+    peers = max(np.abs(g[tag + "/" + n + "_sample"]).max() for n in names)
+    worst = {}
+    for name in names:
+        flat = got[name].reshape(-1).astype(np.float64)
+        step = max(1, flat.size // 1024)
+        ref = g[tag + "/" + name + "_sample"]
+        scale = max(np.abs(ref).max(), 1e-6 * peers)
+        err = np.abs(flat[::step][:1024] - ref).max() / scale
+        worst[name] = err
+        deep = name in ("x", "gconv_w", "bn_w", "bn_b", "l2norm_w")
+        zero_grad = np.abs(ref).max() < 1e-5 * peers                    # conv bias in front of a training-mode BN
+        tol = 2e-2 if deep else 1e-2
+        if zero_grad:
+            assert np.abs(flat).max() <= 1e-2 * peers, (tag, name)
+        else:
+            assert err <= tol, "%s/%s: %.3e of the tensor's scale" % (tag, name, err)
+            sums = g[tag + "/" + name + "_sums"]
+            assert abs(np.abs(flat).sum() - sums[1]) <= 2e-2 * sums[1], (tag, name, "sum of |grad|")
+    print("test_source_block_backward[%s]: worst error / scale per gradient: %s" % (tag, {k: "%.1e" % v for k, v in worst.items()}))
+
+
+def test_source_block_backward_full_size_linearity_and_oracle_sample():
+    """configs[1] size (batch 4 x 38x38 x 512, training-mode BN + L2Norm): the backward is linear in the upstream gradient, and
+    sampled entries of the filter gradients agree with dot products taken by torch from the saved activations"""
+    from grouped_ssd_pytorch_b200.layers import L2Norm, SourceBlock
+    torch.manual_seed(5)
+    N, C, H, A, NC = 4, 512, 38, 4, 2
+    gconv, gbn = nn.Conv2d(C, C, 3, padding=1, groups=4).cuda(), nn.BatchNorm2d(C).cuda()
+    fuse, bnf = nn.Conv2d(C, C, 1).cuda(), nn.BatchNorm2d(C).cuda()
+    l2 = L2Norm(C, 20).cuda()
+    loc, conf = nn.Conv2d(C, A * 4, 3, padding=1).cuda(), nn.Conv2d(C, A * NC, 3, padding=1).cuda()
+    blk = SourceBlock(gconv, gbn, l2, fuse, bnf, loc, conf, num_classes=NC)
+    mods = [gconv, gbn, l2, fuse, bnf, loc, conf]
+    x = torch.relu(torch.randn(N, C, H, H, device="cuda"))
+
+    def grads(up_l, up_c):
+        for m in mods:
+            m.zero_grad()
+        xt = x.clone().requires_grad_()
+        lo, co, xo = blk.forward_autograd(xt)
+        ((lo * up_l).sum() + (co * up_c).sum()).backward()
+        return [xt.grad.clone()] + [p.grad.clone() for m in mods for p in m.parameters()]
+
+    P = H * H * A
+    u1, u2 = torch.randn(N, P, 4, device="cuda"), torch.randn(N, P, NC, device="cuda")
+    v1, v2 = torch.randn(N, P, 4, device="cuda"), torch.randn(N, P, NC, device="cuda")
+    ga, gb, gab = grads(u1, u2), grads(v1, v2), grads(u1 + v1, u2 + v2)
+    for a, b, ab in zip(ga, gb, gab):
+        scale = float(ab.abs().max()) + 1e-12
+        assert float((a + b - ab).abs().max()) <= 3e-2 * scale                # bf16 rounding of the intermediate gradients
+    # against torch autograd on the same modules (fp32 cuDNN), same inputs: the reference semantics at full size
+    for m in mods:
+        m.zero_grad()
+    xt = x.clone().requires_grad_()
+    h = torch.relu(gbn(gconv(xt)))
+    s = torch.relu(bnf(fuse(l2(h))))
+    lo = loc(s).permute(0, 2, 3, 1).reshape(N, -1, 4)
+    co = conf(s).permute(0, 2, 3, 1).reshape(N, -1, NC)
+    ((lo * u1).sum() + (co * u2).sum()).backward()
+    ref = [xt.grad.clone()] + [p.grad.clone() for m in mods for p in m.parameters()]
+    names = ["x"] + [n for m, mn in zip(mods, ["gconv", "bn", "l2norm", "fuse", "bn_fuse", "loc", "conf"]) for n, _ in
+                     [(mn + "." + pn, 0) for pn, _ in m.named_parameters()]]
+    peers = max(float(r.abs().max()) for r in ref)
+    for n, a, r in zip(names, ga, ref):
+        scale = max(float(r.abs().max()), 1e-6 * peers)
+        if float(r.abs().max()) < 1e-5 * peers:
+            continue                                                         # conv bias in front of a training-mode BN
+        err = float((a - r).abs().max()) / scale
+        assert err <= 2e-2, "%s: %.3e of the tensor's scale at the configs[1] size" % (n, err)

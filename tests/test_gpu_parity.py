@@ -468,7 +468,7 @@ def test_detect_from_logits_equals_detect_of_softmax(C, bias):
     assert float((got[..., 0] - want[..., 0]).abs().max()) <= 1.2e-7, "scores differ by more than an ulp"
 
 
-@pytest.mark.parametrize("C,bias,B", [(2, None, 3), (2, (0.0, -4.0), 32), (3, (0.5, -2.0, -3.0), 2)])
+@pytest.mark.parametrize("C,bias,B", [(2, (0.0, -2.5), 3), (2, (0.0, -4.0), 32), (3, (0.5, -2.0, -3.0), 2)])
 def test_detect_from_logits_vs_oracle(C, bias, B):
     """gssd_detect_logits against the ORACLE (not against our own Detect): the oracle's Detect (detection_pytorch_ver_1point5.py:
     33-89) is fed softmax(conf + bias) computed by numpy in torch's formula (row max, exp, sum, divide —
