@@ -132,7 +132,10 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.LIB
-    if _build.stale():
+    alt = os.environ.get("GSSD_LIB")                  # development: an alternative build of the library (A/B measurements)
+    if alt:
+        path = os.path.abspath(alt)
+    elif _build.stale():
         try:
             _build.build()
         except Exception as e:  # no nvcc on this box and no prebuilt library

@@ -115,8 +115,14 @@ __device__ __forceinline__ float softmax_class(const float *row, const float *bi
 // dynamic smem:  [ u32 keys[n] | (aliased later) u32 mask[top_k][words] ]  u64 ckey[max(k2, CAP)]  float4 box[top_k]  float area[top_k]
 // CL: launched as a cluster (small batches: helper CTAs for the bitmask, one round of loads in the threshold pass, registers
 // unconstrained); !CL: two CTAs per SM for machine-filling batches.
+// Both variants are held to 32 registers per thread: a 1024-thread CTA at 64 registers fills an SM's register file, and the
+// loss kernel that runs beside Detect (bench step, training step) then has to wait for those SMs — measured on the batch-32
+// step: 43.0 -> 41.6 us with Detect itself 22.9 -> 23.5 us (profiles/r2_detect_regs_ab.txt).
+#ifndef GSSD_DET_CL_MINB
+#define GSSD_DET_CL_MINB 2
+#endif
 template <bool NMS_MODE, bool CL>
-__global__ void __launch_bounds__(DET_NT, CL ? 1 : 2) detect_kernel(DetArgs a) {
+__global__ void __launch_bounds__(DET_NT, CL ? GSSD_DET_CL_MINB : 2) detect_kernel(DetArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ DetShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -614,6 +614,7 @@ extern "C" int gssd_conv_igemm(const gssd_conv_desc *d, void *stream) {
     } else {
         bn = ng % 256 == 0 ? 256 : (ng % 128 == 0 ? 128 : (ng % 64 == 0 ? 64 : 0));
         if (bn == 0) return GSSD_ERR_LIMIT;
+        if (bn == 256 && d->taps == 9) bn = 128;                 // a filter row of three 256-wide weight tiles leaves no room for the slabs
     }
     const long rows_l = (long)d->n_img * (d->height + 2) * (d->width + 2);
     if (rows_l > (1l << 30)) return GSSD_ERR_LIMIT;

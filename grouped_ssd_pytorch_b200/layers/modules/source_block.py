@@ -516,6 +516,11 @@ class _SourceChainFn(torch.autograd.Function):
                 grads["gconv_w"] = _wgrad(d1, x0, g.c_out, g.groups, g.taps)
                 dx = conv_igemm(d1, dg["g"].cv, relu=False)
             gx = dx if ctx.x_is_pm else dx.to_nchw()
+            if getattr(blk, "_debug_backward", None) is not None:        # development: the intermediate gradients, as NCHW fp32
+                blk._debug_backward.update(dH=dH.to_nchw(), dz2=dz2.to_nchw(), t2=t2.to_nchw(), a1=a1.to_nchw(), z2=z2.to_nchw(),
+                                           y1=y1.to_nchw(), ss=ss)
+                if g is not None:
+                    blk._debug_backward.update(d1=d1.to_nchw())
         out = [None, gx if ctx.needs_input_grad[1] else None]
         for name, prm in blk.param_list():
             gr = grads.get(name)
