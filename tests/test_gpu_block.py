@@ -189,7 +189,7 @@ def _grad_dict(xt, mods):
     return {k: v.detach().double().cpu().numpy() for k, v in got.items()}
 
 
-def _backward_case(tag):
+def _backward_case(tag, with_xout=False):
     """-> (our gradients, torch-autograd gradients through the SAME modules with the ReLU masks of our forward, case)"""
     import torch.nn.functional as F
     from grouped_ssd_pytorch_b200.layers import SourceBlock
@@ -204,7 +204,14 @@ def _backward_case(tag):
     loc, conf, x_out = blk.forward_autograd(xt)
     d_loc, d_conf = cases.block_upstream(tag, loc[0].numel(), conf[0].numel())
     T = lambda a: torch.from_numpy(np.asarray(a, np.float32)).cuda()
-    ((loc.reshape(N, -1) * T(d_loc)).sum() + (conf.reshape(N, -1) * T(d_conf)).sum()).backward()
+    # with_xout: the block's second output (the post-ReLU grouped-conv map that continues down the backbone) takes part too
+    w_out = None
+    if with_xout and x_out is not None:
+        w_out = T(np.random.RandomState(seed + 7).randn(*x_out.shape) * 0.05)
+    total = (loc.reshape(N, -1) * T(d_loc)).sum() + (conf.reshape(N, -1) * T(d_conf)).sum()
+    if w_out is not None:
+        total = total + (x_out * w_out).sum()
+    total.backward()
     torch.cuda.synchronize()
     got = _grad_dict(xt, mods)
     dbg = blk._debug_backward
@@ -230,7 +237,10 @@ def _backward_case(tag):
     z = z * m2
     lo = locm(z).permute(0, 2, 3, 1).reshape(N, -1)
     co = confm(z).permute(0, 2, 3, 1).reshape(N, -1)
-    ((lo * T(d_loc)).sum() + (co * T(d_conf)).sum()).backward()
+    total = (lo * T(d_loc)).sum() + (co * T(d_conf)).sum()
+    if w_out is not None:
+        total = total + (h * w_out).sum()
+    total.backward()
     ref = _grad_dict(xr, mods)
     flips = 0
     with torch.no_grad():
@@ -240,6 +250,20 @@ def _backward_case(tag):
             hh = gbn(hh) if gbn is not None else hh
             flips += int(((hh > 0).float() != m1).sum())
     return got, ref, flips, (x, prm, training)
+
+
+@pytest.mark.parametrize("tag", ["s1_train", "s2", "s1_nobn"])
+def test_source_block_backward_with_the_gradient_of_its_second_output(tag):
+    """the post-ReLU grouped-conv map continues down the backbone (GSSD:300-301): its upstream gradient joins the gradient that
+    comes back through L2Norm / fuse before the ReLU mask and the BatchNorm backward"""
+    got, ref, _, _ = _backward_case(tag, with_xout=True)
+    peers = max(np.abs(v).max() for v in ref.values())
+    for name in sorted(ref):
+        a, r = got[name].reshape(-1), ref[name].reshape(-1)
+        if np.abs(r).max() < 1e-5 * peers:
+            continue
+        err = np.abs(a - r).max() / np.abs(r).max()
+        assert err <= 2e-2, "%s/%s: %.3e of the tensor's scale" % (tag, name, err)
 
 
 @pytest.mark.parametrize("tag", ["s1_train", "s2", "s4", "s1_nobn"])
@@ -312,23 +336,31 @@ def test_source_block_backward_full_size_linearity_and_oracle_sample():
     peers_ab = max(float(t.abs().max()) for t in gab)
     for a, b, ab in zip(ga, gb, gab):
         scale = max(float(ab.abs().max()), 1e-3 * peers_ab)                 # (a conv bias in front of a training-mode BN has no gradient)
-        assert float((a + b - ab).abs().max()) <= 3e-2 * scale                # bf16 rounding of the intermediate gradients
-    # against torch autograd on the same modules (fp32 cuDNN), same inputs: the reference semantics at full size
+        assert float((a + b - ab).abs().max()) <= 5e-2 * scale                # bf16 rounding of the intermediate gradients, three passes
+    # against torch autograd on the same modules (fp32 cuDNN), same inputs, with the ReLU masks of our forward (see
+    # test_source_block_backward): the reference semantics at full size
+    blk._debug_backward = {}
+    grads(u1, u2)
+    m1, m2 = (blk._debug_backward["y1"] > 0).float(), (blk._debug_backward["z2"] > 0).float()
+    blk._debug_backward = None
     for m in mods:
         m.zero_grad()
     xt = x.clone().requires_grad_()
-    h = torch.relu(gbn(gconv(xt)))
-    s = torch.relu(bnf(fuse(l2(h))))
+    h = gbn(gconv(xt)) * m1
+    s = bnf(fuse(l2(h))) * m2
     lo = loc(s).permute(0, 2, 3, 1).reshape(N, -1, 4)
     co = conf(s).permute(0, 2, 3, 1).reshape(N, -1, NC)
     ((lo * u1).sum() + (co * u2).sum()).backward()
     ref = [xt.grad.clone()] + [p.grad.clone() for m in mods for p in m.parameters()]
-    names = ["x"] + [n for m, mn in zip(mods, ["gconv", "bn", "l2norm", "fuse", "bn_fuse", "loc", "conf"]) for n, _ in
-                     [(mn + "." + pn, 0) for pn, _ in m.named_parameters()]]
+    names = ["x"] + [mn + "." + pn for m, mn in zip(mods, ["gconv", "bn", "l2norm", "fuse", "bn_fuse", "loc", "conf"])
+                     for pn, _ in m.named_parameters()]
     peers = max(float(r.abs().max()) for r in ref)
+    worst = {}
     for n, a, r in zip(names, ga, ref):
-        scale = max(float(r.abs().max()), 1e-6 * peers)
         if float(r.abs().max()) < 1e-5 * peers:
             continue                                                         # conv bias in front of a training-mode BN
-        err = float((a - r).abs().max()) / scale
-        assert err <= 2e-2, "%s: %.3e of the tensor's scale at the configs[1] size" % (n, err)
+        worst[n] = float((a - r).abs().max()) / float(r.abs().max())
+    print("full-size backward vs torch autograd with our masks, max error / scale:", {k: "%.1e" % v for k, v in worst.items()})
+    # the maximum is over 3 M entries here: 3e-2 for the tensors behind all five bf16 tensors of the backward, 1e-2 for the rest
+    deep = ("x", "gconv.weight", "gconv.bias", "bn.weight", "bn.bias", "l2norm.weight")
+    assert all(v <= (3e-2 if k in deep else 1e-2) for k, v in worst.items()), worst
