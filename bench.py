@@ -321,7 +321,7 @@ def nrank_parity(a, torch, dist, dev, rank, world, priors, dsets, MultiBoxLoss, 
         return bufs
 
     g_loc, g_conf = gather(d["loc"].detach()), gather(d["conf"].detach())
-    gt, gt_off = d["targets"][0], d["targets"][1]
+    gt, gt_off = d["targets"].gt, d["targets"].gt_off
     # packed ground truth: rows differ per rank -> pad to the global maximum
     n_rows = torch.tensor([gt.shape[0]], device=dev)
     all_rows = [torch.zeros_like(n_rows) for _ in range(world)]

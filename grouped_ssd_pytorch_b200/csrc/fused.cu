@@ -146,8 +146,10 @@ __global__ void __launch_bounds__(NT, NT <= 512 ? 1024 / NT : 1) fused_kernel(Fu
 
     // epoch of this step (read before anybody can have advanced it: it moves when the LAST CTA of the launch exits)
     const bool multi = a.x.world > 0;
-    const uint32_t epoch = (multi ? *reinterpret_cast<const volatile uint32_t *>(&a.x.peers[a.x.rank]->epoch)
-                                  : *reinterpret_cast<const volatile uint32_t *>(&a.state->epoch)) + 1;
+    // two counters: the exchange buffer's (shared by the ranks' kernels of one consumer) tags the words that cross ranks, the
+    // local state's tags everything that stays on this GPU (the state may serve several consumers on one stream)
+    const uint32_t lepoch = *reinterpret_cast<const volatile uint32_t *>(&a.state->epoch) + 1;
+    const uint32_t epoch = multi ? *reinterpret_cast<const volatile uint32_t *>(&a.x.peers[a.x.rank]->epoch) + 1 : lepoch;
     const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
     // this CTA's word of rendezvous `kind` (0: conf max, 1: positives): one plain 8-byte store per destination
     auto publish = [&](int kind, uint32_t value) {
@@ -640,14 +642,14 @@ __global__ void __launch_bounds__(NT, NT <= 512 ? 1024 / NT : 1) fused_kernel(Fu
     if (tid == 0) {
         double l = 0.0, c = 0.0;
         for (int w = 0; w < NW; ++w) { l += s_red[0][w]; c += s_red[1][w]; }
-        *reinterpret_cast<volatile unsigned long long *>(&a.state->slot[2][cta]) = ((unsigned long long)epoch << 32) | __float_as_uint((float)l);
-        *reinterpret_cast<volatile unsigned long long *>(&a.state->slot[3][cta]) = ((unsigned long long)epoch << 32) | __float_as_uint((float)c);
+        *reinterpret_cast<volatile unsigned long long *>(&a.state->slot[2][cta]) = ((unsigned long long)lepoch << 32) | __float_as_uint((float)l);
+        *reinterpret_cast<volatile unsigned long long *>(&a.state->slot[3][cta]) = ((unsigned long long)lepoch << 32) | __float_as_uint((float)c);
     }
     if (cta == 0) {
         double l = 0.0, c = 0.0;
         for (unsigned i = tid; i < n_ctas; i += NT) {
-            l += (double)__uint_as_float(slot_wait(&a.state->slot[2][i], epoch, 4000000000ull));
-            c += (double)__uint_as_float(slot_wait(&a.state->slot[3][i], epoch, 4000000000ull));
+            l += (double)__uint_as_float(slot_wait(&a.state->slot[2][i], lepoch, 4000000000ull));
+            c += (double)__uint_as_float(slot_wait(&a.state->slot[3][i], lepoch, 4000000000ull));
         }
         l = warp_sum(l); c = warp_sum(c);
         __syncthreads();
@@ -660,7 +662,7 @@ __global__ void __launch_bounds__(NT, NT <= 512 ? 1024 / NT : 1) fused_kernel(Fu
             a.losses[1] = __fdiv_rn((float)c, n_f);
             // every CTA has published its last word: the next launch on this state is a new epoch
             if (multi) *reinterpret_cast<volatile uint32_t *>(&a.x.peers[a.x.rank]->epoch) = epoch;
-            else *reinterpret_cast<volatile uint32_t *>(&a.state->epoch) = epoch;
+            *reinterpret_cast<volatile uint32_t *>(&a.state->epoch) = lepoch;
         }
     }
     GSSD_PHASE(fused, 7, dbg);

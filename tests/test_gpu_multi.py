@@ -22,20 +22,28 @@ def _free_port():
 
 
 def _inputs(B=8):
+    B = int(os.environ.get("GSSD_TEST_MULTI_B", B))
     pri = cases.priors("v2")
     r = syn.rng(77)
     tg = syn.targets(r, B, 1, 5)
     return syn.loc(r, B, pri.shape[0]), syn.conf_logits(r, B, pri.shape[0], 2), pri, tg
 
 
-def _run(loc, conf, pri, tg, dev):
+def _run(loc, conf, pri, tg, dev, steps=1):
+    """`steps` calls of the criterion on the same inputs (the exchange's epoch advances every call); returns the last"""
     from grouped_ssd_pytorch_b200.layers import MultiBoxLoss
     crit = MultiBoxLoss(2, 0.5, True, 0, True, 3, 0.5, False, True)
     crit.keep_masks = True
-    l = torch.from_numpy(loc).to(dev).requires_grad_()
-    c = torch.from_numpy(conf).to(dev).requires_grad_()
-    ll, lc = crit((l, c, torch.from_numpy(pri).to(dev)), [torch.from_numpy(t).to(dev) for t in tg])
-    (ll + lc).backward()
+    for k in range(steps + (1 if steps > 1 else 0)):
+        if k == steps:
+            # one more call through a SECOND criterion object on the same stream: its exchange starts at epoch 1 while the
+            # launch counter of the shared local state is at `steps` (bench.py's N-rank check found the two mixed up)
+            crit = MultiBoxLoss(2, 0.5, True, 0, True, 3, 0.5, False, True)
+            crit.keep_masks = True
+        l = torch.from_numpy(loc).to(dev).requires_grad_()
+        c = torch.from_numpy(conf).to(dev).requires_grad_()
+        ll, lc = crit((l, c, torch.from_numpy(pri).to(dev)), [torch.from_numpy(t).to(dev) for t in tg])
+        (ll + lc).backward()
     return ll, lc, l.grad, c.grad, crit.last_masks
 
 
@@ -50,7 +58,7 @@ def _worker(rank, world, port, q, xchg):
     try:
         loc, conf, pri, tg = _inputs()
         sl = gdist.shard(loc.shape[0], rank, world)
-        ll, lc, gl, gc, m = _run(loc[sl], conf[sl], pri, tg[sl], dev)
+        ll, lc, gl, gc, m = _run(loc[sl], conf[sl], pri, tg[sl], dev, steps=3)
         tot = torch.stack([ll.detach(), lc.detach()]).double()
         dist.all_reduce(tot)
         # the native host-buffer pipeline in its two-phase (begin / all-gather / finish) form gives the same step
@@ -75,8 +83,9 @@ def _worker(rank, world, port, q, xchg):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("xchg", ["1", "0"])                     # NVLink peer exchange / NCCL all-gather of the statistics
-def test_two_gpus_match_one_gpu(xchg):
+@pytest.mark.parametrize("xchg,batch", [("1", 8), ("0", 8), ("1", 64), ("1", 300)])   # NVLink peer exchange / NCCL all-gather of the
+def test_two_gpus_match_one_gpu(xchg, batch, monkeypatch):                             # statistics; one-launch / two-launch kernels
+    monkeypatch.setenv("GSSD_TEST_MULTI_B", str(batch))
     import torch.multiprocessing as mp
     from grouped_ssd_pytorch_b200 import dist as gdist
     world = 2
