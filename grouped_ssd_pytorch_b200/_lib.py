@@ -90,6 +90,9 @@ _SIGS = {
     "gssd_detect": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P]),
     "gssd_detect_logits": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P]),
     "gssd_pipe_set_detect_logits": (_I, [_P, _I, _P]),
+    "gssd_collect_detections": (_I, [_P, _I, _I, _I, _I, _F, _F, _F, _I, _P, _P, _P, _P]),
+    "gssd_ap_workspace_bytes": (_SZ, [_I, _I]),
+    "gssd_ap_eval": (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "gssd_l2norm_fwd": (_I, [_P, _P, _I, _I, _I, _F, _P, _P, _P]),
     "gssd_l2norm_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _SZ, _P]),
     "gssd_l2norm_bwd_ws_bytes": (_SZ, [_I, _I, _I]),

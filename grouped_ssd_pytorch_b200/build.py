@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgssd_b200.so")
-SOURCES = ["abi.cu", "boxes.cu", "match.cu", "loss.cu", "fused.cu", "detect.cu", "gconv.cu", "gconv_bwd.cu", "pipe.cu"]
+SOURCES = ["abi.cu", "boxes.cu", "match.cu", "loss.cu", "fused.cu", "detect.cu", "evalap.cu", "gconv.cu", "gconv_bwd.cu", "pipe.cu"]
 HEADERS = ["common.cuh", "select.cuh", "tc.cuh", "tmap.cuh", os.path.join("..", "..", "include", "gssd.h")]
 
 NVCC_FLAGS = [

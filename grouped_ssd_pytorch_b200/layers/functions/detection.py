@@ -102,18 +102,3 @@ class Detect(object):
         with torch.no_grad():
             return _detect(num_classes, top_k, conf_thresh, nms_thresh, loc_data, conf_data, prior_data,
                            cfg['variance'], want_aux=True)
-
-
-def collect_detections(output, width, height, thresh, class_index=1, first_image_id=0):
-    """The consumer of Detect's output in the reference's evaluator, for a whole batch at once (test_ap_iobb.py:124-149, which
-    runs one image at a time on the host): rows of class `class_index` with score > 0, boxes scaled by (width, height, width,
-    height), an image-id column in front, then `score > thresh`.  output: [B, C, top_k, 5] -> float32 CPU array [n, 6] =
-    (image id, score, xmin, ymin, xmax, ymax) in image order, descending score inside an image — the rows the reference
-    accumulates in `all_boxes`.  The filtering runs on the device; one D2H copy."""
-    det = output[:, class_index]                                              # [B, top_k, 5]
-    B, K = det.shape[0], det.shape[1]
-    scale = torch.tensor([1.0, width, height, width, height], dtype=det.dtype, device=det.device)
-    keep = (det[..., 0] > 0) & (det[..., 0] > thresh)                         # test_ap_iobb.py:132-134, 147
-    ids = torch.arange(first_image_id, first_image_id + B, device=det.device, dtype=det.dtype).view(B, 1, 1).expand(B, K, 1)
-    rows = torch.cat([ids, det * scale], dim=-1)[keep]                        # boolean index keeps (image, rank) order
-    return rows.cpu().numpy()

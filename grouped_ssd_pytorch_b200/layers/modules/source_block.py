@@ -644,7 +644,7 @@ def gssd_forward(net, x, detect_args=(0, 200, 0.01, 0.45), backbone=False):
             raise RuntimeError("the sources produced %d priors, the model has %d" % (off, P))
         if use_ag:
             loc, conf = torch.cat(locs, 1), torch.cat(confs, 1)
-        if net.phase == "test":                                  # GSSD:382-390
-            return Detect.apply(net.num_classes, detect_args[0], detect_args[1], detect_args[2], detect_args[3],
-                                loc, torch.softmax(conf, dim=-1), net.priors.to(x.device))
+        if net.phase == "test":                                  # GSSD:382-390: softmax(conf) evaluated inside Detect's threshold pass
+            return Detect.apply_logits(net.num_classes, detect_args[0], detect_args[1], detect_args[2], detect_args[3],
+                                       loc, conf, net.priors.to(x.device))
         return loc, conf, net.priors

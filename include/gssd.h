@@ -415,6 +415,26 @@ GSSD_API int     gssd_pipe_set_xchg(gssd_pipe *p, const gssd_xchg *x_host);
 GSSD_API int     gssd_pipe_wait(gssd_pipe *p, int64_t ticket);
 
 /* ------------------------------------------------------------------------------------------
+ * The consumer of Detect's output in the reference's evaluator (test_ap_iobb.py), on the GPU
+ * ---------------------------------------------------------------------------------------- */
+/* test_ap_iobb.py:126-149 for a whole batch: rows of class `class_index` with score > 0 and score > thresh, boxes scaled by
+ * (width, height, width, height), image id (first_image_id + b) in front -> rows[n,6] = (id, score, x1, y1, x2, y2) in (image,
+ * descending score) order; offsets[B+1] = first row of every image, offsets[B] = n.  rows must hold B*top_k*6 floats. */
+GSSD_API int gssd_collect_detections(const float *detect_out, int B, int C, int top_k, int class_index, float width, float height,
+                            float thresh, int first_image_id, float *rows, int32_t *offsets, int32_t *counts_ws /* [B] */,
+                            void *stream);
+/* test_ap_iobb.py:251-326 + voc_ap (10-41): AP at the IoU thresholds and at the IoBB thresholds (IoBB = intersection over the
+ * DETECTION's area) of rows[n_det,6] grouped by image (det_off[n_img+1]) against gt_boxes[sum_G,4] (gt_off[n_img+1], at most
+ * 128 boxes per image) in the rows' coordinates.  thresholds[n_iou + n_iobb] (IoU ones first), npos = number of ground-truth
+ * boxes, rec_points[11] = np.arange(0., 1.1, 0.1) for the VOC-07 metric.  ap_out[n_iou + n_iobb] float64.  Optional outputs:
+ * tp_out[n_thr][n_det] (1 = true positive, 2 = false positive, 0 = image without boxes) and order_out[n_det] (row indices in
+ * descending score, equal scores in row order).  Float64 arithmetic as in the reference. */
+GSSD_API size_t gssd_ap_workspace_bytes(int n_det, int n_thr);
+GSSD_API int gssd_ap_eval(const float *rows, const int32_t *det_off, const float *gt_boxes, const int32_t *gt_off, int n_img, int n_det,
+                 const double *thresholds, int n_iou, int n_iobb, int npos, int use_07_metric, const double *rec_points,
+                 double *ap_out, uint8_t *tp_out, uint32_t *order_out, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * workspace sizing (host-only)
  * ---------------------------------------------------------------------------------------- */
 enum { GSSD_WS_LSE = 0, GSSD_WS_MATCH = 1, GSSD_WS_LOSS = 2, GSSD_WS_NMS = 3 };

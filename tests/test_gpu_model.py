@@ -59,7 +59,8 @@ def test_gssd_forward_batch_and_test_phase():
     loc, conf, priors = net(xb)
     assert rel(loc[:1].cpu().numpy(), g["loc"]) <= 1e-2          # image 0 is unaffected by its batch neighbour
     ref = Detect.apply(2, 0, 200, 0.01, 0.45, loc, torch.softmax(conf, -1), priors.cuda())
-    assert torch.equal(out, ref)
+    # the test phase evaluates the softmax inside Detect: same boxes, scores to an ulp of torch's softmax kernel
+    assert torch.equal(out[..., 1:], ref[..., 1:]) and float((out[..., 0] - ref[..., 0]).abs().max()) <= 1.2e-7
 
 
 def test_maxpool_pm_equals_torch():
