@@ -734,14 +734,16 @@ def time_kernels(a, lib, _lib, torch, dev, priors, dsets, pack_targets, B, P, it
         for i in range(3):
             fn(i % n_sets)
         torch.cuda.synchronize()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-        torch.cuda._sleep(int(2.5e7))                    # ~13 ms of GPU spin: the host runs ahead
+        # `iters` back-to-back launches between ONE pair of events (an event pair per launch adds ~4 us of its own to a 25 us
+        # kernel), behind ~13 ms of GPU spin so that the host is ahead and no launch waits for it
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(int(2.5e7))
+        e0.record()
         for i in range(iters):
-            ev[i][0].record()
             fn(i % n_sets)
-            ev[i][1].record()
+        e1.record()
         torch.cuda.synchronize()
-        us = statistics.mean(e[0].elapsed_time(e[1]) for e in ev) * 1e3
+        us = e0.elapsed_time(e1) / iters * 1e3
         res.append({"name": name, "us": us, "bytes": nbytes, "gbs": nbytes / us / 1e3})
     return res
 

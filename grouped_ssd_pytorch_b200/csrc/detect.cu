@@ -11,6 +11,8 @@
 // (detection_pytorch_ver_1point5.py:56, 82-84).
 #include <stdlib.h>
 
+#include <math.h>
+
 #include "select.cuh"
 
 GSSD_PHASE_DECL(detect)
@@ -33,6 +35,9 @@ struct DetArgs {
     // logits mode (gssd_detect_logits): conf holds raw class logits, the class score is softmax(conf + bias)[cl]
     int logits;
     float bias[GSSD_MAX_CLASSES];
+    // two classes: a prior whose logit difference (x1 + b1) - (x0 + b0) is below `cull` cannot reach conf_thresh — its score is
+    // sigmoid(difference) up to a few ulp — and skips the exact softmax (two expf and an IEEE divide); -inf switches the test off
+    float cull;
 };
 
 struct DetShared {
@@ -189,8 +194,12 @@ __global__ void __launch_bounds__(DET_NT, CL ? GSSD_DET_CL_MINB : 2) detect_kern
                     const int q = base + u * DET_NT + tid;
                     sv[u] = q < q_hi ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
                     if (a.logits) {                                         // fused softmax: (.y, .w) become the class-1 scores
-                        sv[u].y = softmax2_class1(__fadd_rn(sv[u].x, a.bias[0]), __fadd_rn(sv[u].y, a.bias[1]));
-                        sv[u].w = softmax2_class1(__fadd_rn(sv[u].z, a.bias[0]), __fadd_rn(sv[u].w, a.bias[1]));
+                        const float y0 = __fadd_rn(sv[u].x, a.bias[0]), y1 = __fadd_rn(sv[u].y, a.bias[1]);
+                        const float z0 = __fadd_rn(sv[u].z, a.bias[0]), z1 = __fadd_rn(sv[u].w, a.bias[1]);
+                        // most priors are far below the threshold: 0 stands for "not a candidate" (conf_thresh >= 0 whenever
+                        // cull is finite); the exact torch-formula score is computed for the others only
+                        sv[u].y = __fsub_rn(y1, y0) < a.cull ? 0.f : softmax2_class1(y0, y1);
+                        sv[u].w = __fsub_rn(z1, z0) < a.cull ? 0.f : softmax2_class1(z0, z1);
                     }
                 }
 #pragma unroll
@@ -468,7 +477,10 @@ static int launch_detect(DetArgs &a, dim3 grid, cudaStream_t st) {
         static const int forced = []{ const char *e = getenv("GSSD_DETECT_CLUSTER"); return e ? atoi(e) : 0; }();
         if (forced == 1 || forced == 2 || forced == 4) S = forced;
     }
-    if (!NMS_MODE && S > 1) return launch_detect_as<NMS_MODE, true>(a, grid, S, smem, st);
+    // cluster variant: at 32 registers two of these CTAs would fit one SM, and the scheduler then packs the CTAs of a cluster onto
+    // it (measured: batch 64, 22.7 -> 30.6 us); asking for more than half an SM's shared memory keeps it at one per SM while
+    // leaving room (registers, threads, ~110 KB) for a CTA of the loss kernel beside it
+    if (!NMS_MODE && S > 1) return launch_detect_as<NMS_MODE, true>(a, grid, S, smem > 116 * 1024 ? smem : (size_t)116 * 1024, st);
     return launch_detect_as<NMS_MODE, false>(a, grid, 1, smem, st);
 }
 
@@ -489,6 +501,13 @@ static int detect_impl(const float *loc, const float *conf, const float *class_b
     a.out = out; a.count = count; a.keep_idx = keep_idx;
     a.top_k = top_k; a.nms_thresh = nms_thresh;
     a.logits = logits ? 1 : 0;
+    a.cull = -INFINITY;
+    if (logits && C == 2 && conf_thresh > 0.f && conf_thresh < 1.f) {
+        // score > thr  <=>  logit difference > log(thr / (1 - thr)) in exact arithmetic; the computed score is within a few ulp
+        // (5e-7 relative) of sigmoid(difference), which a margin of 1e-2 in the difference covers with room for every thr <= 0.999 (checked on 4e6 pairs per threshold with torch.softmax)
+        const double l = log((double)conf_thresh / (1.0 - (double)conf_thresh)) - 1e-2;
+        if (1.0 - (double)conf_thresh >= 1e-3) a.cull = nextafterf((float)l, -INFINITY);
+    }
     if (logits && class_bias) for (int c = 0; c < C; ++c) a.bias[c] = class_bias[c];
     return launch_detect<false>(a, dim3(C, B, 1), (cudaStream_t)stream);
 }

@@ -383,8 +383,10 @@ extern "C" int gssd_mbox_scale_grads(float *grad_loc, size_t n_loc, float *grad_
     if (n_loc % 4) return GSSD_ERR_ARG;
     size_t n4c = n_conf / 4; int tail = (int)(n_conf % 4);
     size_t work = (n_loc / 4 > n4c ? n_loc / 4 : n4c);
+    // one CTA per SM: in the usual case (both upstream gradients are 1: `(loss_l + loss_c).backward()`) every CTA only reads the
+    // two scalars and leaves, and the fewer there are to launch and retire the sooner that is over
     int blocks = (int)((work + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > 148) blocks = 148;
     if (blocks < 1) blocks = 1;
     scale_grads_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<float4 *>(grad_loc), n_loc / 4, reinterpret_cast<float4 *>(grad_conf), n4c,
