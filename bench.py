@@ -452,26 +452,30 @@ def run_ours(a):
                     step_device(d)
             torch.cuda.current_stream().wait_stream(cap)
             torch.cuda.synchronize()
-            graphs = []
-            pool = None
-            for d in dsets:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool):
+            # ONE graph holds one step on every input set of the ring, in order, on the stream(s) the API calls use: a replay is
+            # n_sets consecutive steps.  (A graph per step costs a graph launch per 33 us of work: ~10 us of every step.)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for d in dsets:
                     d["result"] = step_device(d)
-                pool = pool or g.pool()
-                graphs.append(g)
+            graphs = g
             torch.cuda.synchronize()
-            dbg('graphs captured')
+            dbg('graph captured: %d steps' % n_sets)
         except Exception as e:                              # pragma: no cover
             sys.stderr.write("bench: CUDA-graph capture failed (%s); timing eager calls\n" % e)
             graphs, use_graph = None, False
             torch.cuda.synchronize()
 
-    def run_step(i):
+    def run_steps(n):
+        """at least n steps, whole ring passes when replaying the graph; returns how many ran"""
         if graphs is not None:
-            graphs[i % n_sets].replay()
-        else:
+            reps = (n + n_sets - 1) // n_sets
+            for _ in range(reps):
+                graphs.replay()
+            return reps * n_sets
+        for i in range(n):
             step_device(dsets[i % n_sets])
+        return n
 
     def barrier():
         if world > 1:
@@ -490,30 +494,25 @@ def run_ours(a):
     # ranks agree on every extra chunk (the steps contain an exchange, so the counts must match)
     K = max(1, a.steps)
     t_w = time.perf_counter()
-    for i in range(max(3, a.warmup)):
-        run_step(i)
+    run_steps(max(3, a.warmup))
     for _ in range(200):
         torch.cuda.synchronize()
         if agree_max(1.0 if time.perf_counter() - t_w < 0.5 else 0.0) == 0.0:
             break
-        for i in range(64):
-            run_step(i)
+        run_steps(64)
     # one untimed round of K steps sizes the timed region: whole rounds of K steps, at least --min-seconds of them
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(K):
-        run_step(i)
+    k_done = run_steps(K)
     e1.record()
     barrier()
-    round_ms = agree_max(e0.elapsed_time(e1))
+    round_ms = agree_max(e0.elapsed_time(e1)) * K / k_done
     rounds = int(max(1, min(10000, math.ceil(a.min_seconds * 1e3 / max(round_ms, 1e-3)))))
-    steps = rounds * K
     dbg('warm-up done; %d rounds of %d steps' % (rounds, K))
     n_launch0 = _lib.launch_count()
     e0.record()
-    for i in range(steps):
-        run_step(i)
+    steps = run_steps(rounds * K)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -625,7 +624,7 @@ def run_ours(a):
             "details": {"steps_arg": K, "rounds_of_steps_arg": rounds,
                         "exchange": "batch-sharded; the 16-byte loss statistics cross ranks as NVLink peer stores issued by the kernels" if world > 1 else "none (1 rank)",
                         "l2_ring": "%d distinct input sets (%.0f MB)" % (n_sets, n_sets * per_set / 1e6),
-                        "launch": ("cuda-graph replay of the public API calls" if graphs is not None else "eager public API calls") + ("; Detect on a second stream beside the loss" if a.mode == "both" else ""),
+                        "launch": ("cuda-graph replay of the public API calls, one graph = one step on each of the ring's input sets" if graphs is not None else "eager public API calls") + ("; Detect on a second stream beside the loss" if a.mode == "both" else ""),
                         "kernels_per_step": kernels_per_step, "host_numa": numa,
                         "targets": "value: packed ground truth resident in HBM; e2e: host list of [n_i,5] tensors packed and copied every step",
                         "detect_scores": "softmax(conf + (0,-4)) evaluated inside the Detect kernel (the CPU arm reads the same scores precomputed)"},

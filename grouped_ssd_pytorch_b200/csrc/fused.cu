@@ -732,6 +732,10 @@ static FusedPlan fused_plan_uncached(int B, int P, int C, int g_max, const void 
                 if (round == 2 && S > 1) continue;
             }
             const int items = ceil_div(n_chunks, S) * FCHUNK;
+            // a CTA that owns more than 24 chunks has too few threads for its IoU sweep: measured, SSD512 priors with up to 32 GT at
+            // batch 64 (S = 2, 48 chunks per CTA) take 94 us in one launch against 41 + 39 us in two, SSD300 priors at batch 64 (S = 2,
+            // 18 chunks) 32 us against 16 + 23 us
+            if (!forced_s && items > 24 * FCHUNK) continue;
             const size_t smem = fused_smem_bytes(g_max, S, items, C);
             if (smem > (size_t)optin - 2048) continue;
             const void *kern = fused_pick(NT, c2, gr);

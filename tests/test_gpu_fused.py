@@ -75,7 +75,7 @@ def _compare(f, t):
 
 
 @pytest.mark.parametrize("B,pname,gmax,C", [(32, "v2", 5, 2), (1, "v2", 5, 2), (3, "v2", 3, 2), (74, "v2", 5, 2), (148, "v2", 2, 2),
-                                            (8, "v2_512", 32, 2), (64, "v2_512", 32, 2), (5, "small", 3, 2), (4, "v2", 6, 4),
+                                            (8, "v2_512", 32, 2), (16, "v2_512", 32, 2), (5, "small", 3, 2), (4, "v2", 6, 4),
                                             (2, "v2_custom_512", 100, 2)])
 def test_fused_equals_two_stage(B, pname, gmax, C):
     f, t, (loc, conf, pri, tg) = _both(B, pname, gmax, C)
