@@ -174,11 +174,23 @@ __global__ void __launch_bounds__(NT, NT <= 512 ? 1024 / NT : 1) fused_kernel(Fu
                 acc = kind == 0 ? max(acc, v) : acc + v;
             }
         } else {
+            // lane r of every warp learns how many CTAs rank r runs (all ranks polled at once: one L2 round trip, not `world` of
+            // them in a row — that chain cost 3 us per rendezvous at 8 ranks), then the warp's threads share the world x CTAs words
             const XBuf *xl = a.x.peers[a.x.rank];
-            for (int r = 0; r < a.x.world; ++r) {
-                const unsigned n_r = slot_wait(&xl->hdr[epoch & 1][r], epoch, a.x.timeout_ns);
-                for (unsigned i = tid; i < n_r; i += NT) {
-                    const uint32_t v = slot_wait(&xl->slot[epoch & 1][kind][r][i], epoch, a.x.timeout_ns);
+            const uint32_t n_mine = lane < a.x.world ? slot_wait(&xl->hdr[epoch & 1][lane], epoch, a.x.timeout_ns) : 0u;
+            uint32_t incl = n_mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+            const uint32_t total = __shfl_sync(FULL, incl, 31);
+            for (uint32_t base = 0; base < total; base += NT) {                 // uniform trip count: the shuffles below need every lane
+                const uint32_t j = base + tid;
+                uint32_t r = 0, first = 0;
+                for (int q = 0; q < a.x.world; ++q) {
+                    const uint32_t end_q = __shfl_sync(FULL, incl, q), n_q = __shfl_sync(FULL, n_mine, q);
+                    if (j >= end_q) { r = q + 1; } else if (j >= end_q - n_q) { r = q; first = end_q - n_q; }
+                }
+                if (j < total) {
+                    const uint32_t v = slot_wait(&xl->slot[epoch & 1][kind][r][j - first], epoch, a.x.timeout_ns);
                     acc = kind == 0 ? max(acc, v) : acc + v;
                 }
             }
