@@ -650,6 +650,11 @@ def run_ours(a):
                 line["gconv"] = time_gconv(a, torch, dev, B)
             except Exception as e:                               # pragma: no cover
                 line["gconv"] = {"error": repr(e)}
+        if not a.no_gconv and world == 1 and a.config == 1:
+            try:
+                line["model_step"] = time_model_step(a, torch, dev, B)
+            except Exception as e:                               # pragma: no cover
+                line["model_step"] = {"error": repr(e)}
         if (a.sweep or (world == 1 and a.config == 1)) and not a.no_sweep:
             line["roofline_sweep"] = sweep(a, lib, _lib, torch, dev, pack_targets)
         print(json.dumps(line), flush=True)
@@ -796,6 +801,57 @@ def time_gconv(a, torch, dev, B):
             "images_per_s": B / (tot_us * 1e-6), "total_us": tot_us,
             "flops_note": "algorithmic flops of the 38x38 interior; the kernel also computes the 1-pixel border (40x40 rows, +10.8%)",
             "kernels": rows}
+
+
+def time_model_step(a, torch, dev, B):
+    """BASELINE.json configs[1] as the reference words it — a GSSD *training step*: model forward, MultiBoxLoss, backward — on a
+    stand-in of the reference model (same constructors and state-dict as models/ssd_multiphase_custom_group.py, tests/gssd_standin.py;
+    seeded random weights, synthetic 4-phase slices).  Two forwards of the same model object: its own torch modules (cuDNN fp32, what
+    the reference runs) and `gssd_forward` (the six source chains on the tcgen05 kernels, forward AND backward); the criterion is
+    ours in both.  Informational: the headline metric is the multibox head, which is 0.1 % of this step."""
+    import types
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import gssd_standin as G
+    from grouped_ssd_pytorch_b200 import config, synthetic as syn
+    from grouped_ssd_pytorch_b200.layers import MultiBoxLoss, PriorBox
+    from grouped_ssd_pytorch_b200.layers.modules.source_block import gssd_forward
+    torch.backends.cudnn.benchmark = True                                   # train_lesion_multiphase_v2.py:594
+    net = G.StandInSSD('train', 2, True, PriorBox(config.v2).forward())
+    net.load_state_dict(G.seeded_state(net.state_dict(), 71))
+    net.to(dev).train()
+    x = G.seeded_input(72, B).to(dev)
+    targets = [torch.from_numpy(t).to(dev) for t in syn.targets(syn.rng(5), B, 1, a.gmax)]
+    crit = MultiBoxLoss(2, MATCH_THRESH, True, 0, True, NEGPOS, 0.5, False, True)
+    crit.process_group = False
+    fast = types.MethodType(gssd_forward, net)
+
+    def ref_forward(xx):
+        loc, conf = G.forward_torch(net, xx)
+        return loc, conf, net.priors
+
+    out = {}
+    for name, fwd in (("torch_forward", ref_forward), ("gssd_forward", fast)):
+        def step():
+            net.zero_grad(set_to_none=True)
+            o = fwd(x)
+            ll, lc = crit(o, targets)
+            (ll + lc).backward()
+            return ll, lc
+        for _ in range(3):
+            ll, lc = step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 8
+        e0.record()
+        for _ in range(n):
+            ll, lc = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        out[name] = {"ms_per_step": ms, "images_per_s": B / (ms * 1e-3), "loss_l": float(ll), "loss_c": float(lc)}
+    out["speedup"] = out["torch_forward"]["ms_per_step"] / out["gssd_forward"]["ms_per_step"]
+    out["workload"] = "GSSD (ssd_type gssd, batch_norm, 8.34 M parameters) training step, batch %d, 4-phase 300x300: forward + MultiBoxLoss + backward, eager" % B
+    return out
 
 
 def sweep(a, lib, _lib, torch, dev, pack_targets):
