@@ -1,7 +1,6 @@
-// wgrad_probe.cu — STAGED for the next round: the weight gradient of the grouped 3x3 convolution of the
-// source block as a tcgen05 kernel, with a host check at a small size and a timing at the configs[1] size.  Standalone on
-// purpose: it has not run yet (written after the round's GPU budget was spent; only its operand encoding was confirmed,
-// tools/umma_mnmajor_probe.cu), so it lives here and not in csrc/gconv.cu.
+// wgrad_probe.cu — the stand-alone prototype of the weight-gradient kernel (grouped 3x3, 128 channels per group) with a host check
+// at small sizes and a timing at the configs[1] size.  Ran green on a B200 at the start of round 2 (profiles/r2_staged_probes.txt:
+// exact, 68.6 us); the library kernel that grew out of it is gssd_conv_wgrad (csrc/gconv_bwd.cu).
 //
 //   dW[g][tap][co][ci] = sum_row dY[row][g*128 + co] * X[row + (dy-1)*(W+2) + (dx-1)][g*128 + ci]      tap = dy*3 + dx
 //
