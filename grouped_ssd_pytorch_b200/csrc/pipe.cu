@@ -30,10 +30,10 @@ size_t layout_slot(const gssd_pipe_cfg &c, uint8_t *base, gssd_pipe_slot *s) {
     auto take = [&](size_t bytes) { uint8_t *ptr = base ? base + off : nullptr; off += align_up(bytes); return ptr; };
     const size_t BP = (size_t)c.B * c.P;
     float *loc = (float *)take(BP * 4 * 4);
-    float *conf = (float *)take(BP * c.C * 4);                               // loc | conf | scores stay adjacent: one H2D when
-    float *scores = (float *)take(BP * c.C * 4);                             // the host buffers are adjacent too
-    float *gt = (float *)take((size_t)c.max_gt_rows * 5 * 4);
+    float *conf = (float *)take(BP * c.C * 4);                               // loc | conf | gt | gt_off stay adjacent: ONE H2D per step
+    float *gt = (float *)take((size_t)c.max_gt_rows * 5 * 4);                // when the host buffers are laid out the same way
     int32_t *gt_off = (int32_t *)take((size_t)(c.B + 1) * 4);
+    float *scores = (float *)take(BP * c.C * 4);
     uint16_t *tags = (uint16_t *)take(BP * 2);
     void *stats = take(gssd_stats_bytes(c.B));
     float *losses = (float *)take(16);
@@ -84,22 +84,27 @@ int64_t begin_step(gssd_pipe *p, const float *loc_h, const float *conf_h, const 
     PIPE_CUDA(cudaStreamWaitEvent(p->s_copy, p->ev_free[k], 0));             // the kernels that read this slot are done
     const bool do_detect = det_h != nullptr && (p->det_logits || scores_h != nullptr);
     const bool have_scores = do_detect && !p->det_logits;
-    const bool adjacent = have_scores && (const uint8_t *)conf_h == (const uint8_t *)loc_h + align_up(n_loc) &&
-                          (const uint8_t *)scores_h == (const uint8_t *)conf_h + align_up(n_conf);
-    const bool adjacent2 = !have_scores && (const uint8_t *)conf_h == (const uint8_t *)loc_h + align_up(n_loc);
-    if (adjacent) {
-        PIPE_CUDA(cudaMemcpyAsync(s.loc, loc_h, align_up(n_loc) + align_up(n_conf) + n_conf, cudaMemcpyHostToDevice, p->s_copy));
-    } else if (adjacent2) {
-        PIPE_CUDA(cudaMemcpyAsync(s.loc, loc_h, align_up(n_loc) + n_conf, cudaMemcpyHostToDevice, p->s_copy));
+    const uint8_t *l8 = (const uint8_t *)loc_h, *c8 = (const uint8_t *)conf_h, *g8 = (const uint8_t *)gt_h, *o8 = (const uint8_t *)gt_off_h;
+    const size_t n_gt_max = align_up((size_t)c.max_gt_rows * 5 * 4);
+    const bool conf_adj = c8 == l8 + align_up(n_loc);
+    // every small copy costs the DMA engine microseconds of its own: with the host buffers in the slot's layout (HostBuffers in
+    // pipeline.py) a step's inputs are ONE transfer — loc | conf | gt rows (up to max_gt_rows) | row offsets
+    const bool all_adj = do_loss && conf_adj && g8 == c8 + align_up(n_conf) && o8 == g8 + n_gt_max;
+    if (all_adj) {
+        PIPE_CUDA(cudaMemcpyAsync(s.loc, loc_h, align_up(n_loc) + align_up(n_conf) + n_gt_max + (size_t)(c.B + 1) * 4, cudaMemcpyHostToDevice, p->s_copy));
     } else {
-        PIPE_CUDA(cudaMemcpyAsync(s.loc, loc_h, n_loc, cudaMemcpyHostToDevice, p->s_copy));
-        PIPE_CUDA(cudaMemcpyAsync(s.conf, conf_h, n_conf, cudaMemcpyHostToDevice, p->s_copy));
-        if (have_scores) PIPE_CUDA(cudaMemcpyAsync(s.scores, scores_h, n_conf, cudaMemcpyHostToDevice, p->s_copy));
+        if (conf_adj) {
+            PIPE_CUDA(cudaMemcpyAsync(s.loc, loc_h, align_up(n_loc) + n_conf, cudaMemcpyHostToDevice, p->s_copy));
+        } else {
+            PIPE_CUDA(cudaMemcpyAsync(s.loc, loc_h, n_loc, cudaMemcpyHostToDevice, p->s_copy));
+            PIPE_CUDA(cudaMemcpyAsync(s.conf, conf_h, n_conf, cudaMemcpyHostToDevice, p->s_copy));
+        }
+        if (do_loss) {
+            PIPE_CUDA(cudaMemcpyAsync(s.gt, gt_h, (size_t)sum_g * 5 * 4, cudaMemcpyHostToDevice, p->s_copy));
+            PIPE_CUDA(cudaMemcpyAsync(s.gt_off, gt_off_h, (size_t)(c.B + 1) * 4, cudaMemcpyHostToDevice, p->s_copy));
+        }
     }
-    if (do_loss) {
-        PIPE_CUDA(cudaMemcpyAsync(s.gt, gt_h, (size_t)sum_g * 5 * 4, cudaMemcpyHostToDevice, p->s_copy));
-        PIPE_CUDA(cudaMemcpyAsync(s.gt_off, gt_off_h, (size_t)(c.B + 1) * 4, cudaMemcpyHostToDevice, p->s_copy));
-    }
+    if (have_scores) PIPE_CUDA(cudaMemcpyAsync(s.scores, scores_h, n_conf, cudaMemcpyHostToDevice, p->s_copy));
     PIPE_CUDA(cudaEventRecord(p->ev_in[k], p->s_copy));
     PIPE_CUDA(cudaStreamWaitEvent(p->s_main, p->ev_in[k], 0));
     const bool fused = do_loss && !two_stage && gssd_mbox_fused_supported(c.B, c.P, c.C, g_max) != 0;

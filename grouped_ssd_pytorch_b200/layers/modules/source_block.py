@@ -160,11 +160,14 @@ def _versions(*mods):
 class _Conv(object):
     """one packed convolution: bf16 weights [c_out(+pad), taps*c_in/groups] + fp32 epilogue vectors"""
 
-    def __init__(self, conv, groups, in_scale=None, extra=None, dev=None):
+    def __init__(self, conv, groups, in_scale=None, extra=None, dev=None, pad_out=None):
         lib = _lib.require_cuda()
         ws = [conv.weight] + ([extra.weight] if extra is not None else [])
         bs = [conv.bias] + ([extra.bias] if extra is not None else [])
         w = torch.cat([_lib.f32(t, dev) for t in ws], 0)
+        self.c_out_real = w.shape[0]
+        if pad_out is not None and w.shape[0] % pad_out:                  # zero filters up to a multiple of `pad_out` output channels
+            w = torch.cat([w, w.new_zeros((pad_out - w.shape[0] % pad_out,) + tuple(w.shape[1:]))], 0)
         kh, kw = conv.kernel_size
         if (kh, kw) not in ((1, 1), (3, 3)) or conv.stride != (1, 1) or conv.dilation != (1, 1) or \
                 conv.padding != ((kh - 1) // 2, (kw - 1) // 2):
@@ -183,6 +186,8 @@ class _Conv(object):
         else:
             self.bias = torch.cat([_lib.f32(b, dev) if b is not None else torch.zeros((t.shape[0],), device=dev)
                                    for b, t in zip(bs, ws)], 0)
+            if self.bias.shape[0] < self.c_out:
+                self.bias = torch.cat([self.bias, self.bias.new_zeros((self.c_out - self.bias.shape[0],))], 0)
         self.scale, self.shift = None, self.bias
 
     def fold_bn(self, bn):
@@ -250,7 +255,12 @@ class SourceBlock(object):
         with torch.no_grad(), torch.cuda.device(dev):
             g = _Conv(self.gconv, self.gconv.groups, dev=dev) if self.gconv is not None else None
             f = _Conv(self.fuse, 1, in_scale=self.l2norm.weight if self.l2norm is not None else None, dev=dev)
-            h = _Conv(self.loc, 1, extra=self.conf, dev=dev)
+            # heads: one launch that scatters straight into loc / conf while their 4A + A*C output channels fit one 64-column tile
+            # (the reference's 2 classes: 24 / 36); wider heads (e.g. 21 VOC classes: 150) run as a plain convolution padded to a
+            # multiple of 64 channels, followed by the permute / flatten of GSSD:376-380 in torch
+            wide = self.loc.out_channels + self.conf.out_channels > 64
+            h = _Conv(self.loc, 1, extra=self.conf, dev=dev, pad_out=64 if wide else None)
+            h.wide = wide
             if not training:
                 if g is not None and self.bn is not None:
                     g.fold_bn(self.bn)
@@ -315,6 +325,17 @@ class SourceBlock(object):
         out = _SourceChainFn.apply(self, x, *prm)
         return (out[0], out[1], out[2] if len(out) > 2 else None)
 
+    def _heads(self, src, h, loc_out, conf_out, prior_off, P):
+        """loc.k / conf.k on `src` (PM) -> this source's slice of loc_out[B,P,4] / conf_out[B,P,C] (GSSD:375-380)"""
+        if not h.wide:
+            conv_igemm(src, h, relu=False, shift=h.bias, head=(loc_out, conf_out, self.n_anchor, self.num_classes, prior_off, P))
+            return
+        y = conv_igemm(src, h, relu=False, shift=h.bias).to_nchw()[:, :h.c_out_real].permute(0, 2, 3, 1)   # [N, H, W, 4A + A*C]
+        n_k = src.h * src.w * self.n_anchor
+        la = 4 * self.n_anchor
+        loc_out[:, prior_off:prior_off + n_k] = y[..., :la].reshape(src.n, n_k, 4)
+        conf_out[:, prior_off:prior_off + n_k] = y[..., la:].reshape(src.n, n_k, self.num_classes)
+
     def forward(self, x, loc_out, conf_out, prior_off):
         """x: NCHW fp32 tensor or PM.  Writes this source's slice of loc_out[B,P,4] / conf_out[B,P,C] (fp32, CUDA) at
         prior offset `prior_off`; returns (x_out PM = the block's post-ReLU grouped-conv output, n_priors_written)."""
@@ -344,8 +365,7 @@ class SourceBlock(object):
                 self._bn_train(src, self.bn_fuse, stats, False)
             else:
                 src = conv_igemm(x1, f, relu=True, scale=f.scale, shift=f.shift, row_ss_in=ss, l2_eps=eps)
-            conv_igemm(src, h, relu=False, shift=h.bias,
-                       head=(loc_out, conf_out, self.n_anchor, self.num_classes, int(prior_off), P))
+            self._heads(src, h, loc_out, conf_out, int(prior_off), P)
         return x1, x.h * x.w * self.n_anchor
 
     __call__ = forward
@@ -413,6 +433,10 @@ class _SourceChainFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             x0 = x if isinstance(x, PM) else PM.from_nchw(x)
             g, f, h, training = blk._pack(dev)
+            if h.wide:
+                raise NotImplementedError("SourceBlock under autograd: heads wider than 64 output channels (%d anchors x (4 + %d classes)); "
+                                          "the forward supports them, the backward is written for the one-tile heads of GSSD"
+                                          % (blk.n_anchor, blk.num_classes))
             want_l2 = blk.l2norm is not None
             eps = blk.l2norm.eps if want_l2 else 0.0
             sv = dict(x0=x0, training=training, l2=want_l2, eps=eps)

@@ -21,19 +21,26 @@ from . import dist as gdist
 
 
 class HostBuffers(object):
-    """page-locked host memory of one step: loc | conf | scores adjacent (one H2D), losses[2], detections[B,C,top_k,5]"""
+    """page-locked host memory of one step in the layout of a pipeline slot — loc | conf | gt rows | row offsets (| scores) — so that
+    a step's inputs travel in ONE H2D transfer; losses[2], detections[B,C,top_k,5]"""
 
-    def __init__(self, B, P, Cn, top_k, with_scores=True):
+    def __init__(self, B, P, Cn, top_k, with_scores=True, max_gt_rows=None):
         a = lambda n: (n + 255) // 256 * 256
         n_loc, n_conf = B * P * 4 * 4, B * P * Cn * 4
-        self.arena = torch.empty((a(n_loc) + a(n_conf) + (n_conf if with_scores else 0),), dtype=torch.uint8).pin_memory()
+        self.max_gt_rows = int(max_gt_rows or B * _lib.MAX_GT_PER_IMAGE)
+        n_gt, n_off = self.max_gt_rows * 5 * 4, (B + 1) * 4
+        o_conf, o_gt = a(n_loc), a(n_loc) + a(n_conf)
+        o_off = o_gt + a(n_gt)
+        o_sc = o_off + a(n_off)
+        self.arena = torch.empty((o_sc + (n_conf if with_scores else 0),), dtype=torch.uint8).pin_memory()
         self.loc = self.arena[:n_loc].view(torch.float32).view(B, P, 4)
-        self.conf = self.arena[a(n_loc):a(n_loc) + n_conf].view(torch.float32).view(B, P, Cn)
-        self.scores = self.arena[a(n_loc) + a(n_conf):].view(torch.float32).view(B, P, Cn) if with_scores else None
+        self.conf = self.arena[o_conf:o_conf + n_conf].view(torch.float32).view(B, P, Cn)
+        self.gt = self.arena[o_gt:o_gt + n_gt].view(torch.float32)
+        self.gt_off = self.arena[o_off:o_off + n_off].view(torch.int32)
+        self.scores = self.arena[o_sc:].view(torch.float32).view(B, P, Cn) if with_scores else None
         self.losses = torch.zeros((2,), dtype=torch.float32).pin_memory()
         self.detections = torch.zeros((B, Cn, top_k, 5), dtype=torch.float32).pin_memory()
-        self.gt = torch.empty((B * _lib.MAX_GT_PER_IMAGE * 5 + B + 1,), dtype=torch.float32).pin_memory()
-        self.gt_np = self.gt.numpy()
+        self.gt_np, self.gt_off_np = self.gt.numpy(), self.gt_off.numpy()
 
 
 class HostPipeline(object):
@@ -74,7 +81,7 @@ class HostPipeline(object):
             _lib.check(lib.gssd_pipe_set_xchg(h, C.byref(self._ex.x)), "gssd_pipe_set_xchg")
 
     def host_buffers(self):
-        return HostBuffers(self.B, self.P, self.C, self.top_k, with_scores=not self.detect_logits)
+        return HostBuffers(self.B, self.P, self.C, self.top_k, with_scores=not self.detect_logits, max_gt_rows=self.cfg.max_gt_rows)
 
     def _pack(self, bufs, targets):
         B = self.B
@@ -88,11 +95,10 @@ class HostPipeline(object):
             raise RuntimeError("HostPipeline: more ground-truth rows than max_gt_rows")
         gt = bufs.gt_np[:sum_g * 5].reshape(sum_g, 5)
         np.concatenate([t.numpy() for t in targets], axis=0, out=gt, casting="unsafe")
-        off = bufs.gt_np[sum_g * 5:sum_g * 5 + B + 1].view(np.int32)
+        off = bufs.gt_off_np
         off[0] = 0
         np.cumsum(lens, out=off[1:])
-        base = bufs.gt.data_ptr()
-        return base, base + sum_g * 5 * 4, sum_g, g_max
+        return bufs.gt.data_ptr(), bufs.gt_off.data_ptr(), sum_g, g_max
 
     def submit(self, bufs, targets, detect=True):
         """enqueue one step on `bufs` (its loc/conf/scores are read, its losses/detections written); returns the ticket.

@@ -103,6 +103,27 @@ def test_source_block_matches_oracle_and_reference(tag):
         assert rel(out[k], g[tag + "/" + k]) <= NORTH_STAR, "%s/%s vs reference: %.3e" % (tag, k, rel(out[k], g[tag + "/" + k]))
 
 
+def test_heads_wider_than_one_tile():
+    """21 classes x 6 anchors = 150 head channels (the VOC configurations of the reference's data/config.py): the heads run as
+    a padded plain convolution + the permute / flatten of GSSD:376-380"""
+    from grouped_ssd_pytorch_b200.layers import SourceBlock
+    torch.manual_seed(2)
+    N, C, H, W, A, NC = 2, 256, 5, 7, 6, 21
+    fuse, loc, conf = nn.Conv2d(C, C, 1).cuda(), nn.Conv2d(C, A * 4, 3, padding=1).cuda(), nn.Conv2d(C, A * NC, 3, padding=1).cuda()
+    blk = SourceBlock(None, None, None, fuse, None, loc, conf, num_classes=NC)
+    x = torch.relu(torch.randn(N, C, H, W, device="cuda"))
+    P = H * W * A + 9
+    lo, co = torch.full((N, P, 4), 7.0, device="cuda"), torch.full((N, P, NC), 7.0, device="cuda")
+    with torch.no_grad():
+        _, n = blk(x, lo, co, 4)
+        s = torch.relu(fuse(x))
+        want_l = loc(s).permute(0, 2, 3, 1).reshape(N, -1, 4)
+        want_c = conf(s).permute(0, 2, 3, 1).reshape(N, -1, NC)
+    assert n == H * W * A and bool((lo[:, :4] == 7).all()) and bool((co[:, 4 + n:] == 7).all())
+    assert rel(lo[:, 4:4 + n].cpu().numpy(), want_l.cpu().numpy()) <= NORTH_STAR
+    assert rel(co[:, 4:4 + n].cpu().numpy(), want_c.cpu().numpy()) <= NORTH_STAR
+
+
 def test_border_of_the_block_output_is_zero():
     out, _, _ = run_block("s1")
     x1 = out["x1"]
