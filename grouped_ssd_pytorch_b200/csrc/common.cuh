@@ -200,20 +200,22 @@ __device__ __forceinline__ float4 decode_box(float4 l, float4 p, float v0, float
 }
 
 // ---- warp / block reductions ---------------------------------------------------------------------
-__device__ __forceinline__ int warp_sum(int v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
+// all 32 lanes must be converged; one CREDUX instruction each on sm_100a (float min / max: redux.sync.f32, new with Blackwell)
+__device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(FULL, v); }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
 __device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
-    return v;
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float warp_min(float v) {
+    float r;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
 }
 
 // split cluster barrier: arrive early (e.g. once the buffers other CTAs will write into are initialised), wait right before

@@ -304,11 +304,7 @@ __global__ void __launch_bounds__(NT, NT <= 512 ? 1024 / NT : 1) fused_kernel(Fu
             const float4 pb = point_form(a.priors[p]);
             bx1 = fminf(bx1, pb.x); by1 = fminf(by1, pb.y); bx2 = fmaxf(bx2, pb.z); by2 = fmaxf(by2, pb.w);
         }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            bx1 = fminf(bx1, __shfl_xor_sync(FULL, bx1, o)); by1 = fminf(by1, __shfl_xor_sync(FULL, by1, o));
-            bx2 = fmaxf(bx2, __shfl_xor_sync(FULL, bx2, o)); by2 = fmaxf(by2, __shfl_xor_sync(FULL, by2, o));
-        }
+        bx1 = warp_min(bx1); by1 = warp_min(by1); bx2 = warp_max(bx2); by2 = warp_max(by2);
         if (lane == 0) { s_bbox[0][warp] = bx1; s_bbox[1][warp] = by1; s_bbox[2][warp] = bx2; s_bbox[3][warp] = by2; }
         __syncthreads();
         if (warp == 0) {
@@ -421,11 +417,7 @@ __global__ void __launch_bounds__(NT, NT <= 512 ? 1024 / NT : 1) fused_kernel(Fu
             for (int q = 0; q < n_list; ++q) sweep_one(glist[q]);
         } else {
             float bx1 = pb.x, by1 = pb.y, bx2 = pb.z, by2 = pb.w;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                bx1 = fminf(bx1, __shfl_xor_sync(FULL, bx1, o)); by1 = fminf(by1, __shfl_xor_sync(FULL, by1, o));
-                bx2 = fmaxf(bx2, __shfl_xor_sync(FULL, bx2, o)); by2 = fmaxf(by2, __shfl_xor_sync(FULL, by2, o));
-            }
+            bx1 = warp_min(bx1); by1 = warp_min(by1); bx2 = warp_max(bx2); by2 = warp_max(by2);
             for (int gb = 0; gb < n_list; gb += 32) {
                 const int q = gb + lane;
                 bool hit = false;
