@@ -124,6 +124,9 @@ _SIGS = {
     "gssd_bn_relu_bwd_pm": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _P, _F, _P, _F, _P, _P, _P]),
     "gssd_bn_act_pm_to": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _I, _P, _P, _P]),
     "gssd_bn_act_pm": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _F, _I, _P, _P, _P]),
+    "gssd_dcn_columns": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "gssd_dcn_columns_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "gssd_pmf32_to_nchw": (_I, [_P, _I, _I, _I, _I, _P, _P]),
 }
 
 _lib = None

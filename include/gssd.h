@@ -357,6 +357,26 @@ GSSD_API int gssd_bn_relu_bwd_pm(const void *dy_bf16, const void *y_bf16, const 
                         void *out_bf16, float *sums, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Modulated deformable convolution (DCNv2) of GSSD++ — replaces `dcn_v2._DCNv2.apply` as called at
+ * layers/dcn_v2_custom.py:49-55 and 84-88 (3x3, stride 1, padding 1, dilation 1).
+ *   forward : gssd_dcn_columns, then gssd_conv_igemm with taps = 1 and c_in = 9*c_in on the columns
+ *   backward: gssd_conv_igemm (d_columns = dY * W), gssd_conv_wgrad (dW = dY^T * columns), gssd_dcn_columns_bwd
+ * x: PM bf16 [rows, c_in]; offset fp32 [n_img, 2*dg*9, H, W] with channel (g*9 + tap)*2 = dy, +1 = dx; mask fp32
+ * [n_img, dg*9, H, W] (already sigmoid-ed by the caller, dcn_v2_custom.py:83); dg = deformable groups; c_in/dg must be a
+ * multiple of 8.  columns: bf16 [rows, 9*c_in], k = tap*c_in + c — the K order of gssd_conv_pack_weights(taps = 9,
+ * groups = 1), so the packed 3x3 filter IS the 1x1 filter over the columns; border rows are written as zeros.
+ * A sample at (y, x) is zero unless -1 < y < H and -1 < x < W; neighbours outside the image count as zero.
+ * ---------------------------------------------------------------------------------------- */
+GSSD_API int gssd_dcn_columns(const void *x_bf16, const float *offset, const float *mask, int n_img, int c_in, int height, int width,
+                     int deformable_groups, void *col_bf16, void *stream);
+/* d_columns bf16 [rows, 9*c_in] -> dx_pm fp32 PM [rows, c_in] (zeroed by the call, then accumulated with vector reductions:
+ * the summation order, hence the last bits, vary from run to run), d_offset / d_mask in the layouts of offset / mask */
+GSSD_API int gssd_dcn_columns_bwd(const void *x_bf16, const float *offset, const float *mask, const void *dcol_bf16, int n_img, int c_in,
+                         int height, int width, int deformable_groups, float *dx_pm, float *d_offset, float *d_mask, void *stream);
+/* fp32 PM [rows, c] -> NCHW fp32 (the interior pixels) */
+GSSD_API int gssd_pmf32_to_nchw(const float *x_pm, int n_img, int c, int h, int w, float *y, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Host-buffer pipeline — the training-step / inference call of the hot path with HOST inputs and outputs:
  * the H2D of train_lesion_multiphase_v2.py:198-200, the criterion call at :246 (MultiBoxLoss forward + the
  * gradients of its two outputs) and Detect (ssd_multiphase_custom_group.py:384-390), `depth` steps in flight:

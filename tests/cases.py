@@ -142,3 +142,29 @@ def block_upstream(tag, n_loc, n_conf):
     seed, N = BLOCK_CASES[tag][0], BLOCK_CASES[tag][1]
     r = np.random.RandomState(seed + 1000)
     return r.randn(N, n_loc), r.randn(N, n_conf)
+
+
+# ---- GSSD++'s modulated deformable convolution (layers/dcn_v2_custom.py) ----------------------------------------------------------
+# tag -> (seed, N, C_in, C_out, H, W, deformable groups, scale of the offset convolution's weights; 0 = the module's own
+# zero initialisation (dcn_v2_custom.py:72-74): offsets exactly 0, masks exactly 0.5, samples ON the pixel grid and on y = -1)
+DCN_CASES = {
+    "rand": (501, 2, 128, 64, 7, 7, 4, 0.02),
+    "zero": (502, 1, 128, 64, 5, 6, 2, 0.0),
+    "wide": (503, 1, 128, 64, 9, 5, 1, 0.05),          # large offsets: many samples leave the image
+}
+
+
+def dcn_case(tag):
+    """-> dict(x, weight, bias, com_w, com_b, gout, dg): inputs, the parameters of a `DCN` module (dcn_v2_custom.py:58-88) and
+    the upstream gradient of its output."""
+    seed, N, C, O, H, W, dg, s = DCN_CASES[tag]
+    r = np.random.RandomState(seed)
+    f = lambda *shape: r.standard_normal(shape).astype(np.float32)
+    return dict(x=f(N, C, H, W), weight=f(O, C, 3, 3) / np.float32(np.sqrt(9 * C)), bias=0.1 * f(O),
+                com_w=np.float32(s) * f(dg * 27, C, 3, 3), com_b=(np.float32(s * 10) * f(dg * 27)), gout=f(N, O, H, W), dg=dg)
+
+
+def strided_sample(a, stride=5):
+    """what the DCN fixture keeps of a large gradient: every `stride`-th element, the sum and the absolute sum"""
+    a = np.asarray(a, np.float64).ravel()
+    return np.concatenate([a[::stride], [a.sum(), np.abs(a).sum()]])
