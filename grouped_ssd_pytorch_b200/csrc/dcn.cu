@@ -13,7 +13,7 @@
 // they are small against the GEMM: 9*c_in*2 bytes per pixel written once and read once, 18 KB at c_in = 1024, for
 // 2*9*c_in*c_out = 9.4 MFLOP per pixel at c_out = 512 — 520 flop/byte, far on the tensor side of the ridge.
 //
-// Sampling rule (the pinned oracle is torchvision.ops.deform_conv2d, the stand-in SURVEY App. A names; it agrees with DCNv2's
+// Sampling rule (parity is pinned against torchvision.ops.deform_conv2d, the stand-in SURVEY App. A names; it agrees with DCNv2's
 // dmcn_im2col_bilinear): a sample at (y, x) is 0 unless -1 < y < H and -1 < x < W; inside, the four neighbours floor/floor+1
 // contribute (1-ly)(1-lx), (1-ly)lx, ly(1-lx), ly*lx, neighbours outside the image count as 0.  PM's zero border IS that rule
 // for every in-range sample, so the gather needs one predicate.  The offset gradient follows torchvision's

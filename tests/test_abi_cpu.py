@@ -190,7 +190,7 @@ import layers, data
 ours = "grouped_ssd_pytorch_b200"
 assert MultiBoxLoss.__module__.startswith(ours) and Detect.__module__.startswith(ours) and PriorBox.__module__.startswith(ours)
 assert L2Norm.__module__.startswith(ours) and match.__module__.startswith(ours)
-assert self_attn.__file__.startswith(%(ref)r) and DCN.__module__ == "layers.dcn_v2_custom"
+assert self_attn.__file__.startswith(%(ref)r) and DCN.__module__.startswith(ours)      # GSSD++'s DCN on our kernels
 assert data.__file__.startswith(%(ref)r), "the reference's data package must stay the one that is imported"
 from models.ssd_multiphase_custom_group import build_ssd
 import torch
@@ -201,6 +201,8 @@ tst = build_ssd('test', 300, 2, True, 4, 4, 1, True, False, False, 0, 1, False, 
 assert type(tst.detect).__module__.startswith(ours)
 pp = build_ssd('train', 300, 2, True, 4, 4, 1, True, True, True, 1, 4, True, False, 1)               # GSSD++ (SA + DCN)
 assert sum(p.numel() for p in pp.parameters()) == 18488172
+assert type(pp.dcn_list[0]).__module__.startswith(ours) and sorted(n for n, _ in pp.dcn_list[0].named_parameters()) == [
+    "bias", "conv_offset_mask.bias", "conv_offset_mask.weight", "weight"]                                # the reference's state-dict names
 crit = MultiBoxLoss(2, 0.5, True, 0, True, 3, 0.5, False, True)                                      # train_lesion_multiphase_v2.py:639
 print("DROPIN-OK")
 """
