@@ -24,10 +24,10 @@ def _reference_layers_dir(own_dir, reference_root=None):
 def install_as_layers(provide_data=True, reference_root=None, reference_modules=()):
     """Make `layers` (layers/__init__.py:1-2 of the reference) resolve to this package for code imported AFTER the call:
     `layers`, `layers.box_utils`, `layers.functions[.prior_box|.detection|.detection_pytorch_ver_1point5]`,
-    `layers.modules[.l2norm|.multibox_loss]` and `layers.dcn_v2_custom` (GSSD++'s deformable convolution on this library's
-    kernels instead of the un-vendored `dcn_v2` extension) become ours; every other submodule of the reference's package —
-    `layers.self_attn`, `layers.spectral_norm` (models/ssd_multiphase_custom_group.py:6) — stays importable from the
-    reference tree, which is appended to the package search path when it is found on sys.path (or under `reference_root`,
+    `layers.modules[.l2norm|.multibox_loss]`, `layers.dcn_v2_custom` (GSSD++'s deformable convolution on this library's
+    kernels instead of the un-vendored `dcn_v2` extension) and `layers.self_attn` (its attention core on this library's
+    kernels) become ours; every other submodule of the reference's package — `layers.spectral_norm` — stays importable from
+    the reference tree, which is appended to the package search path when it is found on sys.path (or under `reference_root`,
     the directory that holds the reference's `layers/`).  `data` is provided (as our prior-box config module) only when no
     `data` package is importable at all, so that the reference's `from data import DataSplitter, ...`
     (train_lesion_multiphase_v2.py:14) keeps working.  `reference_modules` names submodules (e.g. "dcn_v2_custom") that
@@ -36,7 +36,7 @@ def install_as_layers(provide_data=True, reference_root=None, reference_modules=
     import os
     import sys
     from . import layers as _layers
-    from .layers import dcn_v2_custom as _dcn  # noqa: F401  (imported here so that it is aliased below)
+    from .layers import dcn_v2_custom as _dcn, self_attn as _sa  # noqa: F401  (imported here so that they are aliased below)
     own_dir = os.path.dirname(os.path.abspath(_layers.__file__))
     ref_dir = _reference_layers_dir(own_dir, reference_root)
     if ref_dir is not None and ref_dir not in list(_layers.__path__):
@@ -49,7 +49,7 @@ def install_as_layers(provide_data=True, reference_root=None, reference_modules=
         if ref_dir is None or not os.path.abspath(f).startswith(ref_dir) or name in (
                 "layers", "layers.box_utils", "layers.functions", "layers.modules", "layers.functions.prior_box",
                 "layers.functions.detection", "layers.functions.detection_pytorch_ver_1point5", "layers.modules.l2norm",
-                "layers.modules.multibox_loss", "layers.dcn_v2_custom"):
+                "layers.modules.multibox_loss", "layers.dcn_v2_custom", "layers.self_attn"):
             del sys.modules[name]
     sys.modules["layers"] = _layers
     for name, mod in list(sys.modules.items()):

@@ -377,6 +377,20 @@ GSSD_API int gssd_dcn_columns_bwd(const void *x_bf16, const float *offset, const
 GSSD_API int gssd_pmf32_to_nchw(const float *x_pm, int n_img, int c, int h, int w, float *y, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Attention core of GSSD++'s Self_Attn — replaces layers/self_attn.py:69-81 (permute + bmm + softmax + permute + bmm):
+ *   attn[b, n, m]   = softmax_m( sum_d theta[b, d, n] * phi[b, d, m] )        theta [B, D, N], phi [B, D, M]
+ *   attn_g[b, c, n] = sum_m g[b, c, m] * attn[b, n, m]                         g [B, Cv, M]
+ * fp32, contiguous, the layouts the module's .view() calls produce (self_attn.py:62, 68, 77).  D and Cv must be multiples of 32;
+ * a strip of queries against all keys has to fit in shared memory (M, N up to ~7000).  One kernel forward, two backward.
+ * Backward: gradients of theta / phi / g from d_attn_g [B, Cv, N] and the saved attn; ds_ws [B, N, M] floats of scratch.  The
+ * attention map is an output for inspection only (self_attn.py:86): no gradient is taken through it.
+ * ---------------------------------------------------------------------------------------- */
+GSSD_API int gssd_attn_fwd(const float *theta, const float *phi, const float *g, int B, int D, int Cv, int N, int M, float *attn,
+                  float *attn_g, void *stream);
+GSSD_API int gssd_attn_bwd(const float *theta, const float *phi, const float *g, const float *attn, const float *d_attn_g, int B, int D,
+                  int Cv, int N, int M, float *d_theta, float *d_phi, float *d_g, float *ds_ws, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Host-buffer pipeline — the training-step / inference call of the hot path with HOST inputs and outputs:
  * the H2D of train_lesion_multiphase_v2.py:198-200, the criterion call at :246 (MultiBoxLoss forward + the
  * gradients of its two outputs) and Detect (ssd_multiphase_custom_group.py:384-390), `depth` steps in flight:

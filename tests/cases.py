@@ -168,3 +168,28 @@ def strided_sample(a, stride=5):
     """what the DCN fixture keeps of a large gradient: every `stride`-th element, the sum and the absolute sum"""
     a = np.asarray(a, np.float64).ravel()
     return np.concatenate([a[::stride], [a.sum(), np.abs(a).sum()]])
+
+
+# ---- GSSD++'s Self_Attn block (layers/self_attn.py) -----------------------------------------------------------------------------
+# tag -> (seed, B, C, H, max_pool_factor)
+SA_CASES = {
+    "full": (601, 2, 256, 5, 1),          # keys = queries (the configuration GSSD++ trains with, max_pool_factor 1)
+    "pooled": (602, 1, 256, 6, 2),        # 3 x 3 pooled keys against 36 queries
+    "single": (603, 2, 256, 1, 4),        # the 1 x 1 map of the last source: one query, one key
+}
+
+
+def sa_case(tag):
+    """-> (x, state dict of a Self_Attn module (the reference's names), upstream gradients of its first two outputs)"""
+    seed, B, C, H, _ = SA_CASES[tag]
+    r = np.random.RandomState(seed)
+    f = lambda *shape: r.standard_normal(shape).astype(np.float32)
+    prm = {"sigma": np.float32([0.7])}
+    for name, co, ci in (("snconv1x1_theta", C // 8, C), ("snconv1x1_phi", C // 8, C), ("snconv1x1_g", C // 2, C), ("snconv1x1_attn", C, C // 2)):
+        w, u = f(co, ci, 1, 1) / np.float32(np.sqrt(ci)), f(co)
+        for _ in range(8):                                   # a few power iterations, as a trained module's buffers would hold
+            v = w.reshape(co, ci).T @ u; v /= np.linalg.norm(v)
+            u = w.reshape(co, ci) @ v; u /= np.linalg.norm(u)
+        prm[name + ".weight_orig"], prm[name + ".bias"] = w, 0.1 * f(co)
+        prm[name + ".weight_u"], prm[name + ".weight_v"] = u.astype(np.float32), v.astype(np.float32)
+    return f(B, C, H, H), prm, (f(B, C, H, H), f(B, C, H, H))

@@ -190,7 +190,9 @@ import layers, data
 ours = "grouped_ssd_pytorch_b200"
 assert MultiBoxLoss.__module__.startswith(ours) and Detect.__module__.startswith(ours) and PriorBox.__module__.startswith(ours)
 assert L2Norm.__module__.startswith(ours) and match.__module__.startswith(ours)
-assert self_attn.__file__.startswith(%(ref)r) and DCN.__module__.startswith(ours)      # GSSD++'s DCN on our kernels (SURVEY f4)
+assert self_attn.__name__.startswith(ours) and DCN.__module__.startswith(ours)          # GSSD++'s DCN / Self_Attn on our kernels (SURVEY f4)
+from layers import spectral_norm as _sn
+assert _sn.__file__.startswith(%(ref)r)                                                   # the rest of the reference's package stays importable
 assert data.__file__.startswith(%(ref)r), "the reference's data package must stay the one that is imported"
 from models.ssd_multiphase_custom_group import build_ssd
 import torch
@@ -203,6 +205,9 @@ pp = build_ssd('train', 300, 2, True, 4, 4, 1, True, True, True, 1, 4, True, Fal
 assert sum(p.numel() for p in pp.parameters()) == 18488172
 assert type(pp.dcn_list[0]).__module__.startswith(ours) and sorted(n for n, _ in pp.dcn_list[0].named_parameters()) == [
     "bias", "conv_offset_mask.bias", "conv_offset_mask.weight", "weight"]                                # the reference's state-dict names
+assert type(pp.self_attn_list[0]).__module__.startswith(ours) and type(pp.self_attn_base_list[0]).__module__.startswith(ours)
+assert sorted(pp.self_attn_list[0].state_dict()) == sorted(
+    ["sigma"] + ["snconv1x1_%%s.%%s" %% (c, n) for c in ("theta", "phi", "g", "attn") for n in ("bias", "weight_orig", "weight_u", "weight_v")])
 crit = MultiBoxLoss(2, 0.5, True, 0, True, 3, 0.5, False, True)                                      # train_lesion_multiphase_v2.py:639
 print("DROPIN-OK")
 """

@@ -8,7 +8,7 @@ REF = next(p for p in ("/root/reference/ssd_liverdet", os.path.join(ROOT, "basel
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, REF)
 import torch
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-mode = sys.argv[2] if len(sys.argv) > 2 else "ours"
+mode = sys.argv[2] if len(sys.argv) > 2 else "ours"          # ours | ref | dcn (our DCN, the reference's Self_Attn)
 mpl = types.ModuleType("matplotlib"); mpl.use = lambda *a, **k: None
 sys.modules["matplotlib"] = mpl; sys.modules["matplotlib.pyplot"] = types.ModuleType("matplotlib.pyplot")
 import grouped_ssd_pytorch_b200 as gssd
@@ -21,6 +21,8 @@ if mode == "ref":
             return deform_conv2d(inp, off, w, b, stride=stride, padding=pad, dilation=dil, mask=mask)
     dcn._DCNv2 = _DCNv2; sys.modules["dcn_v2"] = dcn
     gssd.install_as_layers(reference_modules=("dcn_v2_custom", "self_attn"))
+elif mode == "dcn":
+    gssd.install_as_layers(reference_modules=("self_attn",))
 else:
     gssd.install_as_layers()
 from models.ssd_multiphase_custom_group import build_ssd
@@ -45,6 +47,8 @@ for _ in range(5):
     step()
 torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
 print("GSSD++ step, batch %d, %s: %.2f ms (%.0f images/s)" % (B, mode, dt * 1e3, B / dt))
+if os.environ.get("NO_PROFILE"):
+    sys.exit(0)
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     step(); torch.cuda.synchronize()
