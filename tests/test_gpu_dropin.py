@@ -150,12 +150,43 @@ print("DROPIN-GPU-OK", e_loc, e_conf, n_det)
 
 GSSDPP_CASE = PRELUDE + r"""
 # BASELINE.json configs[2]: GSSD++ (self-attention + DCN, groups_dcn 4, one DCN layer) forward + loss (+ backward), 4 images
-# per GPU: the reference's own forward with this repository's `layers`; Self_Attn / DCN stay the reference's modules (SURVEY §8 f4)
+# per GPU: the reference's own forward with this repository's `layers` — including its Self_Attn blocks (attention core on
+# gssd_attn_fwd / gssd_attn_bwd) and its deformable convolution (gssd_dcn_columns + the tcgen05 GEMM), SURVEY §8 f4
 import time
 net = build_ssd('train', 300, 2, True, 4, 4, 1, True, True, True, 1, 4, True, False, 1)
 assert sum(p.numel() for p in net.parameters()) == 18488172
+ours = "grouped_ssd_pytorch_b200"
+assert type(net.dcn_list[0]).__module__.startswith(ours) and all(type(m).__module__.startswith(ours) for m in list(net.self_attn_list) + list(net.self_attn_base_list))
 torch.manual_seed(3)
-net.cuda().train()
+net.cuda()
+# 0. the same network with the REFERENCE's own Self_Attn / DCN classes (its files, loaded beside ours; DCN operator = torchvision's
+# deform_conv2d) on the same parameters: the forward agrees within the tolerance of the bf16 convolution path
+import copy, importlib.util
+def _ref_module(name):
+    spec = importlib.util.spec_from_file_location("ref_" + name, os.path.join(REF, "layers", name + ".py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod); return mod
+ref_sa, ref_dcn = _ref_module("self_attn"), _ref_module("dcn_v2_custom")
+with torch.no_grad():                                   # non-trivial gates / offsets (both are zero-initialised: self_attn.py:43, dcn_v2_custom.py:72-74)
+    for m in list(net.self_attn_list) + list(net.self_attn_base_list):
+        m.sigma.fill_(0.5)
+    net.dcn_list[0].conv_offset_mask.weight.normal_(0, 0.01); net.dcn_list[0].conv_offset_mask.bias.normal_(0, 0.3)
+twin = copy.deepcopy(net)
+def _swap(lst, make):
+    for i, m in enumerate(lst):
+        r = make(m).cuda(); r.load_state_dict(m.state_dict()); lst[i] = r
+_swap(twin.self_attn_list, lambda m: ref_sa.Self_Attn(m.in_channels, m.max_pool_factor))
+_swap(twin.self_attn_base_list, lambda m: ref_sa.Self_Attn(m.in_channels, m.max_pool_factor))
+_swap(twin.dcn_list, lambda m: ref_dcn.DCN(m.in_channels, m.out_channels, 3, 1, 1, deformable_groups=m.deformable_groups))
+assert not type(twin.dcn_list[0]).__module__.startswith(ours) and not type(twin.self_attn_list[0]).__module__.startswith(ours)
+net.eval(); twin.eval()
+xe = torch.rand(2, 12, 300, 300, device="cuda")
+with torch.no_grad():
+    (l1, c1, _), (l0, c0, _) = net(xe), twin(xe)
+e_f4 = (rel(l1.cpu().numpy(), l0.cpu().numpy()), rel(c1.cpu().numpy(), c0.cpu().numpy()))
+print("GSSD++ forward, this package's Self_Attn / DCN vs the reference's own classes on the same parameters: relative error loc %%.1e conf %%.1e" %% e_f4)
+assert max(e_f4) <= 1e-2, e_f4
+del twin
+net.train()
 B = 4
 x = torch.rand(B, 12, 300, 300, device="cuda")
 tg = syn.targets(syn.rng(9), B, 1, 5)
@@ -187,7 +218,8 @@ assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.para
 tot, head = min(t[0] for t in ts), min(t[1] for t in ts)
 print("GSSDPP-OK configs[2] on one GPU's share (4 images): forward + MultiBoxLoss + backward %%.2f ms (%%.0f images/s per GPU); the multibox head "
       "alone (criterion forward + backward to loc / conf, host-timed eager calls) %%.3f ms = %%.2f %%%% of the step; the rest is the "
-      "reference's torch model (cuDNN grouped convs, Self_Attn bmm, torchvision deform_conv2d)" %% (tot * 1e3, B / tot, head * 1e3, 100 * head / tot))
+      "reference's torch model (cuDNN grouped convs) with this package's Self_Attn / DCN inside; forward vs the reference's own "
+      "Self_Attn / DCN classes: loc %%.1e conf %%.1e" %% (tot * 1e3, B / tot, head * 1e3, 100 * head / tot, e_f4[0], e_f4[1]))
 """
 
 
