@@ -655,6 +655,11 @@ def run_ours(a):
                 line["model_step"] = time_model_step(a, torch, dev, B)
             except Exception as e:                               # pragma: no cover
                 line["model_step"] = {"error": repr(e)}
+        if not a.no_gconv and world == 1 and a.config == 1:
+            try:
+                line["gssdpp"] = time_gssdpp(torch, dev)
+            except Exception as e:                               # pragma: no cover
+                line["gssdpp"] = {"error": repr(e)}
         if (a.sweep or (world == 1 and a.config == 1)) and not a.no_sweep:
             line["roofline_sweep"] = sweep(a, lib, _lib, torch, dev, pack_targets)
         print(json.dumps(line), flush=True)
@@ -801,6 +806,69 @@ def time_gconv(a, torch, dev, B):
             "images_per_s": B / (tot_us * 1e-6), "total_us": tot_us,
             "flops_note": "algorithmic flops of the 38x38 interior; the kernel also computes the 1-pixel border (40x40 rows, +10.8%)",
             "kernels": rows}
+
+
+def time_gssdpp(torch, dev, B=4):
+    """SURVEY f4 at configs[2]'s per-GPU share (4 images): GSSD++'s deformable convolution (1024 -> 512 channels, 38 x 38, 4
+    deformable groups) and the attention core of its Self_Attn blocks (C = 512, 38 x 38) on this library's kernels against the
+    operators the reference runs them on here — torchvision's fp32 deform_conv2d (stand-in of the un-vendored dcn_v2) and
+    torch's bmm + softmax + bmm — forward and forward + backward, CUDA events."""
+    from torchvision.ops import deform_conv2d
+    from grouped_ssd_pytorch_b200.layers import dcn_v2_custom as D, self_attn as S
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    def timed(fn, iters=10, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e3
+
+    def fwd_and_step(fn, leaves, gout):
+        def step():
+            for t in leaves:
+                t.grad = None
+            fn().backward(gout)
+        with torch.no_grad():
+            f = timed(fn)
+        return f, timed(step)
+
+    torch.manual_seed(1111)
+    C, O, H, dg = 1024, 512, 38, 4
+    x = torch.randn(B, C, H, H, device=dev, requires_grad=True)
+    w = (torch.randn(O, C, 3, 3, device=dev) / (9 * C) ** 0.5).requires_grad_(True)
+    b = torch.zeros(O, device=dev, requires_grad=True)
+    off = (1.5 * torch.randn(B, 2 * dg * 9, H, H, device=dev)).requires_grad_(True)
+    msk = torch.sigmoid(torch.randn(B, dg * 9, H, H, device=dev)).requires_grad_(True)
+    gout = torch.randn(B, O, H, H, device=dev)
+    ours = fwd_and_step(lambda: D.dcn_v2_conv(x, off, msk, w, b, 1, 1, 1, dg), (x, w, b, off, msk), gout)
+    ref = fwd_and_step(lambda: deform_conv2d(x, off, w, b, stride=1, padding=1, dilation=1, mask=msk), (x, w, b, off, msk), gout)
+    flops = 2.0 * B * H * H * O * 9 * C
+    out = {"workload": "configs[2] per-GPU share: %d images; DCN 1024->512 ch 38x38 dg 4; Self_Attn core C 512 38x38 (N = M = 1444)" % B,
+           "dcn": {"fwd_us": ours[0], "fwd_bwd_us": ours[1], "ref_fwd_us": ref[0], "ref_fwd_bwd_us": ref[1], "ref": "torchvision.ops.deform_conv2d fp32",
+                   "fwd_tflops_algorithmic": flops / ours[0] / 1e6, "speedup_fwd": ref[0] / ours[0], "speedup_fwd_bwd": ref[1] / ours[1]}}
+    Cs, N = 512, H * H
+    th = (0.5 * torch.randn(B, Cs // 8, N, device=dev)).requires_grad_(True)
+    ph = torch.randn(B, Cs // 8, N, device=dev, requires_grad=True)
+    g = torch.randn(B, Cs // 2, N, device=dev, requires_grad=True)
+    d_o = torch.randn(B, Cs // 2, N, device=dev)
+
+    def ref_core():
+        attn = torch.softmax(torch.bmm(th.permute(0, 2, 1), ph), -1)               # self_attn.py:71-72
+        return torch.bmm(g, attn.permute(0, 2, 1))                                 # :80
+    ours = fwd_and_step(lambda: S.attention_core(th, ph, g)[0], (th, ph, g), d_o)
+    ref = fwd_and_step(ref_core, (th, ph, g), d_o)
+    out["self_attn_core"] = {"fwd_us": ours[0], "fwd_bwd_us": ours[1], "ref_fwd_us": ref[0], "ref_fwd_bwd_us": ref[1],
+                             "ref": "torch bmm + softmax + bmm, fp32 (cuBLAS SIMT)", "launches": "1 forward + 2 backward (reference: 5 + 8 aten kernels)",
+                             "speedup_fwd": ref[0] / ours[0], "speedup_fwd_bwd": ref[1] / ours[1]}
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    return out
 
 
 def time_model_step(a, torch, dev, B):
