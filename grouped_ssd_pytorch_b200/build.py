@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgssd_b200.so")
-SOURCES = ["abi.cu", "boxes.cu", "match.cu", "loss.cu", "fused.cu", "detect.cu", "evalap.cu", "gconv.cu", "gconv_bwd.cu", "dcn.cu", "attn.cu", "pipe.cu"]
+SOURCES = ["abi.cu", "boxes.cu", "match.cu", "loss.cu", "fused.cu", "detect.cu", "evalap.cu", "gconv.cu", "gconv_bwd.cu", "dcn.cu", "attn.cu", "bnrelu.cu", "pipe.cu"]
 HEADERS = ["common.cuh", "select.cuh", "tc.cuh", "tmap.cuh", os.path.join("..", "..", "include", "gssd.h")]
 
 NVCC_FLAGS = [
@@ -24,7 +24,7 @@ NVCC_FLAGS = [
 ]
 # gconv*.cu / dcn.cu (bf16 tensor-core path, 1e-2 tolerance) and attn.cu (fp32 dot products, 1e-5) carry no bit-exact contract:
 # FMA contraction allowed
-PER_SOURCE_FLAGS = {"gconv.cu": ["-fmad=true"], "gconv_bwd.cu": ["-fmad=true"], "dcn.cu": ["-fmad=true"], "attn.cu": ["-fmad=true"]}
+PER_SOURCE_FLAGS = {"gconv.cu": ["-fmad=true"], "gconv_bwd.cu": ["-fmad=true"], "dcn.cu": ["-fmad=true"], "attn.cu": ["-fmad=true"], "bnrelu.cu": ["-fmad=true"]}
 
 
 def _nvcc():

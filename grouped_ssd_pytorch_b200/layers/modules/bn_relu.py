@@ -1,0 +1,85 @@
+"""Training-mode `nn.BatchNorm2d` + `F.relu` of the backbone layers that stay NCHW fp32 torch convolutions
+(models/ssd_multiphase_custom_group.py:434-460, 254-259, 300-301) as one autograd node on `gssd_bn_relu_nchw_fwd / _bwd`:
+two streaming kernels forward, two backward, the ReLU mask recomputed from the input — against cuDNN's batch-norm kernels plus the
+separate ReLU / threshold_backward passes torch runs (the largest cost of the reference's batch-32 training step on a B200).
+
+`bn_relu(x, bn, relu=True)` uses the module's own parameters and updates its running statistics / `num_batches_tracked` exactly as
+`bn(x)` would; evaluation mode, CPU tensors, non-fp32 inputs and `momentum=None` modules are not taken (the caller keeps torch's
+modules for those).  `run_layers(modules, x)` walks a slice of an `nn.ModuleList` / `nn.Sequential` and fuses every
+(BatchNorm2d, ReLU) pair it meets."""
+import torch
+import torch.nn as nn
+
+from ... import _lib
+
+
+class _BnReluTrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, relu):
+        lib = _lib.require_cuda()
+        dev = x.device
+        xc = x.contiguous()
+        N, C = xc.shape[0], xc.shape[1]
+        HW = xc.numel() // (N * C)
+        y = torch.empty_like(xc)
+        save = torch.empty((2 * C,), dtype=torch.float32, device=dev)
+        ws = torch.empty((2 * C,), dtype=torch.float64, device=dev)
+        w, b = _lib.f32(weight, dev), _lib.f32(bias, dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.gssd_bn_relu_nchw_fwd(xc.data_ptr(), w.data_ptr(), b.data_ptr(), N, C, HW, float(eps), 1 if relu else 0,
+                                                 y.data_ptr(), save.data_ptr(), _lib.ptr(running_mean), _lib.ptr(running_var),
+                                                 float(momentum), ws.data_ptr(), _lib.stream()), "gssd_bn_relu_nchw_fwd")
+        ctx.save_for_backward(xc, w, b, save)
+        ctx.relu = relu
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        lib = _lib.require_cuda()
+        xc, w, b, save = ctx.saved_tensors
+        dev = xc.device
+        N, C = xc.shape[0], xc.shape[1]
+        HW = xc.numel() // (N * C)
+        dyc = _lib.f32(dy, dev)
+        dx = torch.empty_like(xc)
+        dg, db = torch.empty_like(w), torch.empty_like(b)
+        ws = torch.empty((2 * C,), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.gssd_bn_relu_nchw_bwd(xc.data_ptr(), dyc.data_ptr(), w.data_ptr(), b.data_ptr(), save.data_ptr(), N, C, HW,
+                                                 1 if ctx.relu else 0, dx.data_ptr(), dg.data_ptr(), db.data_ptr(), ws.data_ptr(),
+                                                 _lib.stream()), "gssd_bn_relu_nchw_bwd")
+        return dx, dg, db, None, None, None, None, None
+
+
+def takes(x, bn):
+    """whether `bn_relu` serves this call (else the caller runs the torch modules)"""
+    return (isinstance(bn, nn.BatchNorm2d) and bn.training and bn.affine and bn.momentum is not None and bn.track_running_stats
+            and isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.numel() > 0)
+
+
+def bn_relu(x, bn, relu=True):
+    """relu(bn(x)) for a training-mode nn.BatchNorm2d `bn` (its running statistics and num_batches_tracked are updated)."""
+    if not takes(x, bn):
+        raise NotImplementedError("bn_relu takes training-mode affine nn.BatchNorm2d with running statistics on CUDA fp32 NCHW input")
+    y = _BnReluTrain.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu)
+    with torch.no_grad():
+        bn.num_batches_tracked += 1
+    return y
+
+
+def run_layers(modules, x, start=0, stop=None):
+    """x through modules[start:stop]; every training-mode (BatchNorm2d, ReLU) pair runs as one fused node, a BatchNorm2d without a
+    ReLU behind it as the same kernels without the clamp, everything else as the module itself."""
+    stop = len(modules) if stop is None else stop
+    k = start
+    while k < stop:
+        m = modules[k]
+        if takes(x, m):
+            fuse = k + 1 < stop and isinstance(modules[k + 1], nn.ReLU)
+            x = bn_relu(x, m, relu=fuse)
+            k += 2 if fuse else 1
+        else:
+            x = m(x)
+            k += 1
+    return x

@@ -593,9 +593,17 @@ def gssd_forward(net, x, detect_args=(0, 200, 0.01, 0.45), backbone=False):
     at 1.0e-2 / 6.6e-3 relative error on loc / conf instead of 6.0e-3 / 3.7e-3 (tests/test_gpu_model.py).
     """
     import contextlib
+    import os
     import torch.nn.functional as F
     from ..functions import Detect
+    from .bn_relu import bn_relu, run_layers, takes as bn_takes
     _lib.require_cuda()
+    fuse_bn = os.environ.get("GSSD_FUSED_BN", "1") != "0"    # development: A/B against torch's BatchNorm2d + ReLU modules
+
+    def _plain(mods, xx, a, b):
+        for kk in range(a, b):
+            xx = mods[kk](xx)
+        return xx
     cache = getattr(net, "_gssd_blocks", None)
     if cache is None:
         cache = build_source_blocks(net)
@@ -643,23 +651,27 @@ def gssd_forward(net, x, detect_args=(0, 200, 0.01, 0.45), backbone=False):
             x = run(x1, i43 + (3 if bn else 2), i7)              # GSSD:300-301 up to the input of conv7
             x2 = run_block(blocks[1], x)                         # conv7 .. heads of source 2 (GSSD:300-325)
         else:
-            for k in range(i43):                                 # GSSD:254-259, up to the input of conv4_3
-                x = net.vgg[k](x)
+            # the backbone layers in between stay the model's torch convolutions / pools; in training mode every (BatchNorm2d, ReLU)
+            # pair behind them runs as one fused node (bn_relu.py: the largest cost of the reference's training step)
+            x = run_layers(net.vgg, x, 0, i43) if fuse_bn else _plain(net.vgg, x, 0, i43)      # GSSD:254-259, up to the input of conv4_3
             x1 = run_block(blocks[0], x)                         # conv4_3 .. heads of source 1 (GSSD:258-297, 375-377)
             x = x1 if use_ag else x1.to_nchw()                   # post-ReLU conv4_3 continues down the backbone
-            for k in range(i43 + (3 if bn else 2), i7):          # GSSD:300-301 up to the input of conv7
-                x = net.vgg[k](x)
+            k0 = i43 + (3 if bn else 2)                          # GSSD:300-301 up to the input of conv7
+            x = run_layers(net.vgg, x, k0, i7) if fuse_bn else _plain(net.vgg, x, k0, i7)
             x2 = run_block(blocks[1], x)                         # conv7 .. heads of source 2 (GSSD:300-325)
         x = x2 if use_ag else x2.to_nchw()
         si = 2
         for k, v in enumerate(net.extras):                       # GSSD:329-372
-            x = v(x)
-            if bn:
+            if bn and k % 2 == 1 and fuse_bn and bn_takes(x, v):
+                x = bn_relu(x, v, relu=True)
+                is_source = k % 4 == 3
+            elif bn:
+                x = v(x)
                 if k % 2 == 1:
                     x = F.relu(x, inplace=True)
                 is_source = k % 4 == 3
             else:
-                x = F.relu(x, inplace=True)
+                x = F.relu(v(x), inplace=True)
                 is_source = k % 2 == 1
             if is_source:
                 run_block(blocks[si], x)

@@ -357,6 +357,21 @@ GSSD_API int gssd_bn_relu_bwd_pm(const void *dy_bf16, const void *y_bf16, const 
                         void *out_bf16, float *sums, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Training-mode BatchNorm2d (+ ReLU) on NCHW fp32 — the "-> BN -> ReLU" behind every grouped backbone convolution that stays a
+ * torch convolution (models/ssd_multiphase_custom_group.py:434-460, applied at :254-259 and :300-301): nn.BatchNorm2d in training
+ * mode (batch statistics, biased variance for the normalisation, running statistics updated with `momentum` and the UNBIASED
+ * variance) followed by F.relu, as two streaming kernels forward and two backward.
+ *   x, y, dy, dx: [N, C, HW] contiguous; gamma / beta [C]; save_mean_rstd [2C] (mean, 1/sqrt(var+eps) per channel, written by the
+ *   forward, read by the backward); running_mean / running_var [C] or both NULL; ws: 2C doubles of scratch (zeroed by the call).
+ *   backward: the ReLU mask is recomputed from x (y > 0  <=>  x*a + b > 0 with the forward's own coefficients).
+ * ---------------------------------------------------------------------------------------- */
+GSSD_API int gssd_bn_relu_nchw_fwd(const float *x, const float *gamma, const float *beta, int N, int C, int HW, float eps, int relu,
+                          float *y, float *save_mean_rstd, float *running_mean, float *running_var, float momentum, double *ws,
+                          void *stream);
+GSSD_API int gssd_bn_relu_nchw_bwd(const float *x, const float *dy, const float *gamma, const float *beta, const float *save_mean_rstd,
+                          int N, int C, int HW, int relu, float *dx, float *d_gamma, float *d_beta, double *ws, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Modulated deformable convolution (DCNv2) of GSSD++ — replaces `dcn_v2._DCNv2.apply` as called at
  * layers/dcn_v2_custom.py:49-55 and 84-88 (3x3, stride 1, padding 1, dilation 1).
  *   forward : gssd_dcn_columns, then gssd_conv_igemm with taps = 1 and c_in = 9*c_in on the columns

@@ -1,0 +1,121 @@
+"""Training-mode BatchNorm2d + ReLU of the NCHW backbone layers on gssd_bn_relu_nchw_fwd / _bwd (layers/modules/bn_relu.py):
+against the numpy oracle (oracle/source_block.py: batch_norm / batch_norm_backward, pinned against the reference's own modules)
+and against torch's nn.BatchNorm2d + F.relu in fp32 — outputs, input / weight / bias gradients, running statistics,
+num_batches_tracked — on vectorised and scalar plane sizes, with and without the ReLU, and through `run_layers` on a slice of a
+backbone-like nn.ModuleList."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from grouped_ssd_pytorch_b200 import _lib
+from grouped_ssd_pytorch_b200.layers.modules.bn_relu import bn_relu, run_layers, takes
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel(a, ref):
+    a, ref = a.detach().double().cpu().numpy(), np.asarray(ref.detach().double().cpu().numpy() if isinstance(ref, torch.Tensor) else ref, np.float64)
+    return float(np.abs(a - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+@pytest.mark.parametrize("shape,relu", [((4, 16, 30, 30), True), ((2, 8, 5, 7), True), ((3, 4, 1, 1), True), ((2, 12, 38, 38), False),
+                                         ((8, 64, 150, 150), True)])
+def test_bn_relu_vs_torch_and_oracle(shape, relu):
+    torch.manual_seed(sum(shape))
+    N, C, H, W = shape
+    x = (torch.randn(shape, device=DEV) * 1.7 + 0.4).requires_grad_(True)
+    bn_a, bn_b = nn.BatchNorm2d(C).to(DEV).train(), nn.BatchNorm2d(C).to(DEV).train()
+    with torch.no_grad():
+        bn_a.weight.uniform_(0.5, 1.5); bn_a.bias.normal_(0, 0.3); bn_a.running_mean.normal_(); bn_a.running_var.uniform_(0.5, 2)
+    bn_b.load_state_dict(bn_a.state_dict())
+    gout = torch.randn(shape, device=DEV)
+    n0 = _lib.launch_count()
+    y = bn_relu(x, bn_a, relu=relu)
+    y.backward(gout)
+    assert _lib.launch_count() == n0 + 4, "two kernels forward, two backward"
+    gx, x.grad = x.grad, None
+    yr = bn_b(x)
+    yr = F.relu(yr) if relu else yr
+    yr.backward(gout)
+    errs = dict(y=rel(y, yr), dx=rel(gx, x.grad), dw=rel(bn_a.weight.grad, bn_b.weight.grad), db=rel(bn_a.bias.grad, bn_b.bias.grad),
+                rm=rel(bn_a.running_mean, bn_b.running_mean), rv=rel(bn_a.running_var, bn_b.running_var))
+    print(shape, relu, {k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) <= 2e-5, errs
+    assert int(bn_a.num_batches_tracked) == int(bn_b.num_batches_tracked) == 1
+    if N * C * H * W <= 100000:                                            # the oracle in float64
+        from oracle import source_block as SB
+        xn = x.detach().cpu().numpy().astype(np.float64)
+        g, b = bn_b.weight.detach().cpu().numpy().astype(np.float64), bn_b.bias.detach().cpu().numpy().astype(np.float64)
+        mean, var = xn.mean((0, 2, 3)), xn.var((0, 2, 3))
+        yo = SB.batch_norm(xn, g, b, mean, var, bn_b.eps, True)[0].astype(np.float64)
+        go = gout.cpu().numpy().astype(np.float64)
+        if relu:
+            go = go * (yo > 0)
+            yo = np.maximum(yo, 0)
+        dxo = SB.batch_norm_backward(xn, g, mean, var, bn_b.eps, True, go)
+        dxo = dxo[0] if isinstance(dxo, tuple) else dxo
+        assert rel(y, torch.from_numpy(yo)) <= 2e-5 and rel(gx, torch.from_numpy(dxo)) <= 5e-5
+
+
+def test_run_layers_fuses_pairs_and_leaves_the_rest():
+    torch.manual_seed(3)
+    mods = nn.ModuleList([nn.Conv2d(12, 16, 3, padding=1, groups=4), nn.BatchNorm2d(16), nn.ReLU(inplace=True), nn.MaxPool2d(2, 2),
+                          nn.Conv2d(16, 32, 3, padding=1, groups=4), nn.BatchNorm2d(32), nn.ReLU(inplace=True)]).to(DEV).train()
+    import copy
+    ref = copy.deepcopy(nn.Sequential(*mods))                               # torch's own modules on the same parameters
+    x = torch.randn(3, 12, 20, 20, device=DEV, requires_grad=True)
+    n0 = _lib.launch_count()
+    y = run_layers(mods, x)
+    y.square().sum().backward()
+    assert _lib.launch_count() == n0 + 8                                    # two fused pairs
+    gx, x.grad = x.grad, None
+    yr = ref(x)
+    yr.square().sum().backward()
+    assert rel(y, yr) <= 2e-5 and rel(gx, x.grad) <= 1e-4
+    for (n, p), (_, q) in zip(mods.named_parameters(), ref.named_parameters()):
+        if n in ("0.bias", "4.bias"):                                       # a convolution's bias in front of a training-mode BatchNorm has
+            continue                                                        # no gradient (BN removes the mean): rounding noise on both sides
+        assert rel(p.grad, q.grad) <= 1e-4, n
+    mods.eval()
+    assert not takes(x, mods[1])                                            # evaluation mode stays torch's
+    with torch.no_grad():
+        assert rel(run_layers(mods, x), ref.eval()(x)) <= 1e-3              # (running statistics after one step agree)
+
+
+def test_bn_relu_argument_errors():
+    bn = nn.BatchNorm2d(4).to(DEV).eval()
+    with pytest.raises(NotImplementedError):
+        bn_relu(torch.randn(1, 4, 3, 3, device=DEV), bn)
+    lib = _lib.load()
+    assert lib.gssd_bn_relu_nchw_fwd(None, None, None, 1, 4, 9, 1e-5, 1, None, None, None, None, 0.1, None, None) == _lib.ERR_ARG
+
+
+def test_bn_relu_bandwidth_at_the_backbone_size():
+    """conv1_x of the batch-32 training step: [32, 64, 300, 300] fp32 (737 MB).  Reported, and held to twice cuDNN's speed."""
+    x = torch.randn(32, 64, 300, 300, device=DEV, requires_grad=True)
+    gout = torch.randn_like(x)
+    bn = nn.BatchNorm2d(64).to(DEV).train()
+
+    def timed(fn, iters=5):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    def ours():
+        x.grad = None
+        bn_relu(x, bn).backward(gout)
+
+    def ref():
+        x.grad = None
+        F.relu(bn(x)).backward(gout)
+    t_o, t_r = timed(ours), timed(ref)
+    gb = x.numel() * 4 * 8 / 1e9                                            # 3 passes forward, 5 backward
+    print("BN + ReLU forward + backward at [32, 64, 300, 300]: ours %.2f ms (%.0f GB/s of the 8 algorithmic passes), torch / cuDNN %.2f ms" % (t_o, gb / t_o * 1e3, t_r))
+    assert t_o < t_r

@@ -153,6 +153,7 @@ GSSDPP_CASE = PRELUDE + r"""
 # per GPU: the reference's own forward with this repository's `layers` — including its Self_Attn blocks (attention core on
 # gssd_attn_fwd / gssd_attn_bwd) and its deformable convolution (gssd_dcn_columns + the tcgen05 GEMM), SURVEY §8 f4
 import time
+torch.manual_seed(2)                                   # the model's initialisation is part of the case
 net = build_ssd('train', 300, 2, True, 4, 4, 1, True, True, True, 1, 4, True, False, 1)
 assert sum(p.numel() for p in net.parameters()) == 18488172
 ours = "grouped_ssd_pytorch_b200"
@@ -169,6 +170,14 @@ ref_sa, ref_dcn = _ref_module("self_attn"), _ref_module("dcn_v2_custom")
 with torch.no_grad():                                   # non-trivial gates / offsets (both are zero-initialised: self_attn.py:43, dcn_v2_custom.py:72-74)
     for m in list(net.self_attn_list) + list(net.self_attn_base_list):
         m.sigma.fill_(0.5)
+    # spectral norm's u / v start as random unit vectors, for which u^T W v is a random number near zero and W / (u^T W v) arbitrarily
+    # large; the evaluation-mode comparison below needs them where training leaves them (one power iteration per training forward):
+    for m in net.modules():
+        if hasattr(m, "weight_u"):
+            w2 = m.weight_orig.reshape(m.weight_orig.shape[0], -1)
+            for _ in range(8):
+                m.weight_v.copy_(torch.nn.functional.normalize(w2.t() @ m.weight_u, dim=0))
+                m.weight_u.copy_(torch.nn.functional.normalize(w2 @ m.weight_v, dim=0))
     net.dcn_list[0].conv_offset_mask.weight.normal_(0, 0.01); net.dcn_list[0].conv_offset_mask.bias.normal_(0, 0.3)
 twin = copy.deepcopy(net)
 def _swap(lst, make):
