@@ -6,8 +6,9 @@
 // although they are plain streaming work: a [32, 64, 300, 300] fp32 activation is 737 MB, the forward needs three passes over it
 // (statistics; read + write) and the backward five (two reductions' inputs; x, dy, dx), 0.34 / 0.57 ms at the HBM roofline against
 // 0.68 / 1.86 ms (+ the ReLU passes) measured for the library kernels.  HBM-bound: one CTA per (image, channel) plane, 16-byte
-// loads and stores, fp32 partial sums per thread, double atomics per channel; the ReLU mask is recomputed from x in the backward
-// (same fused multiply-add as the forward), so the activations are not read again.
+// loads and stores (scalar head / tail where a plane does not start or end on 16 bytes), fp32 partial sums per thread, double
+// atomics per channel; the ReLU mask is recomputed from x in the backward (same fused multiply-add as the forward), so the
+// activations are not read again.  Also here: the backward of the max pools between those layers as a gather (below).
 #include "common.cuh"
 
 namespace gssd {
@@ -43,31 +44,38 @@ __device__ __forceinline__ BnCoef bn_coef(const double *sums, int c, double inv_
     return k;
 }
 
+// One plane = HW contiguous floats starting `off` floats into a 16-byte-aligned tensor: scalar head up to the next 16-byte boundary,
+// float4 body, scalar tail (75 x 75 and 19 x 19 planes are not multiples of four floats: a scalar-only version ran those layers at a
+// third of the bandwidth).  f1(i): element i; f4(i): elements i..i+3, i is 16-byte aligned.
+template <typename F1, typename F4>
+__device__ __forceinline__ void plane_loop(int HW, size_t off, bool aligned, F1 f1, F4 f4) {
+    const int head = aligned ? min(HW, (int)((4 - (off & 3)) & 3)) : HW;
+    for (int i = threadIdx.x; i < head; i += BNR_NT) f1(i);
+    const int n4 = (HW - head) >> 2;
+    for (int i = threadIdx.x; i < n4; i += BNR_NT) f4(head + 4 * i);
+    for (int i = head + 4 * n4 + threadIdx.x; i < HW; i += BNR_NT) f1(i);
+}
+
 // ---- forward -----------------------------------------------------------------------------------------------------
-template <bool VEC>
-__global__ void __launch_bounds__(BNR_NT) bnr_stats_kernel(const float *__restrict__ x, int C, int HW, double *__restrict__ sums) {
-    const size_t plane = blockIdx.x;
-    const float *p = x + plane * HW;
+__global__ void __launch_bounds__(BNR_NT) bnr_stats_kernel(const float *__restrict__ x, int C, int HW, bool aligned, double *__restrict__ sums) {
+    const size_t plane = blockIdx.x, off = plane * HW;
+    const float *p = x + off;
     float s = 0.f, ss = 0.f;
-    if (VEC) {
-        const float4 *p4 = reinterpret_cast<const float4 *>(p);
-        for (int i = threadIdx.x; i < HW / 4; i += BNR_NT) {
-            const float4 v = __ldg(p4 + i);
-            s += (v.x + v.y) + (v.z + v.w);
-            ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-        }
-    } else {
-        for (int i = threadIdx.x; i < HW; i += BNR_NT) { const float v = __ldg(p + i); s += v; ss += v * v; }
-    }
+    plane_loop(HW, off, aligned,
+               [&](int i) { const float v = __ldg(p + i); s += v; ss += v * v; },
+               [&](int i) {
+                   const float4 v = __ldg(reinterpret_cast<const float4 *>(p + i));
+                   s += (v.x + v.y) + (v.z + v.w);
+                   ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+               });
     block_sum2_to_double(s, ss, sums + 2 * (plane % C));
 }
 
-template <bool VEC>
-__global__ void __launch_bounds__(BNR_NT) bnr_apply_kernel(const float *__restrict__ x, int C, int HW, const double *__restrict__ sums,
+__global__ void __launch_bounds__(BNR_NT) bnr_apply_kernel(const float *__restrict__ x, int C, int HW, bool aligned, const double *__restrict__ sums,
                                                            double inv_count, double unbias, float eps, const float *__restrict__ gamma,
                                                            const float *__restrict__ beta, int relu, float *__restrict__ y,
                                                            float *__restrict__ save, float *running_mean, float *running_var, float momentum) {
-    const size_t plane = blockIdx.x;
+    const size_t plane = blockIdx.x, off = plane * HW;
     const int c = (int)(plane % C);
     const BnCoef k = bn_coef(sums, c, inv_count, eps, gamma, beta);
     if (plane < (size_t)C && threadIdx.x == 0) {                           // the planes of image 0 publish the channel's statistics
@@ -80,79 +88,86 @@ __global__ void __launch_bounds__(BNR_NT) bnr_apply_kernel(const float *__restri
             running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * unbias);
         }
     }
-    const float *p = x + plane * HW;
-    float *q = y + plane * HW;
+    const float *p = x + off;
+    float *q = y + off;
     const float lo = relu ? 0.f : -INFINITY;
-    if (VEC) {
-        const float4 *p4 = reinterpret_cast<const float4 *>(p);
-        float4 *q4 = reinterpret_cast<float4 *>(q);
-        for (int i = threadIdx.x; i < HW / 4; i += BNR_NT) {
-            const float4 v = __ldcs(p4 + i);
-            float4 o;
-            o.x = fmaxf(fmaf(v.x, k.a, k.b), lo); o.y = fmaxf(fmaf(v.y, k.a, k.b), lo);
-            o.z = fmaxf(fmaf(v.z, k.a, k.b), lo); o.w = fmaxf(fmaf(v.w, k.a, k.b), lo);
-            q4[i] = o;
-        }
-    } else {
-        for (int i = threadIdx.x; i < HW; i += BNR_NT) q[i] = fmaxf(fmaf(__ldcs(p + i), k.a, k.b), lo);
-    }
+    plane_loop(HW, off, aligned,
+               [&](int i) { q[i] = fmaxf(fmaf(__ldcs(p + i), k.a, k.b), lo); },
+               [&](int i) {
+                   const float4 v = __ldcs(reinterpret_cast<const float4 *>(p + i));
+                   *reinterpret_cast<float4 *>(q + i) = make_float4(fmaxf(fmaf(v.x, k.a, k.b), lo), fmaxf(fmaf(v.y, k.a, k.b), lo),
+                                                                    fmaxf(fmaf(v.z, k.a, k.b), lo), fmaxf(fmaf(v.w, k.a, k.b), lo));
+               });
 }
 
 // ---- backward ----------------------------------------------------------------------------------------------------
 // g = dy where the forward's output was positive (recomputed: x*a + b > 0); sums: (sum g, sum g*x_hat) per channel
-template <bool VEC>
-__global__ void __launch_bounds__(BNR_NT) bnr_bwd_reduce_kernel(const float *__restrict__ x, const float *__restrict__ dy, int C, int HW,
+__global__ void __launch_bounds__(BNR_NT) bnr_bwd_reduce_kernel(const float *__restrict__ x, const float *__restrict__ dy, int C, int HW, bool aligned,
                                                                 const float *__restrict__ save, const float *__restrict__ gamma,
                                                                 const float *__restrict__ beta, int relu, double *__restrict__ sums) {
-    const size_t plane = blockIdx.x;
+    const size_t plane = blockIdx.x, off = plane * HW;
     const int c = (int)(plane % C);
     const float mean = save[2 * c], rstd = save[2 * c + 1], a = rstd * gamma[c], b = beta[c] - mean * a;
-    const float *p = x + plane * HW, *d = dy + plane * HW;
+    const float *p = x + off, *d = dy + off;
     float sg = 0.f, sgx = 0.f;
     auto one = [&](float xv, float dv) {
         const float g = (!relu || fmaf(xv, a, b) > 0.f) ? dv : 0.f;
         sg += g;
         sgx += g * ((xv - mean) * rstd);
     };
-    if (VEC) {
-        const float4 *p4 = reinterpret_cast<const float4 *>(p), *d4 = reinterpret_cast<const float4 *>(d);
-        for (int i = threadIdx.x; i < HW / 4; i += BNR_NT) {
-            const float4 v = __ldg(p4 + i), w = __ldg(d4 + i);
-            one(v.x, w.x); one(v.y, w.y); one(v.z, w.z); one(v.w, w.w);
-        }
-    } else {
-        for (int i = threadIdx.x; i < HW; i += BNR_NT) one(__ldg(p + i), __ldg(d + i));
-    }
+    plane_loop(HW, off, aligned,
+               [&](int i) { one(__ldg(p + i), __ldg(d + i)); },
+               [&](int i) {
+                   const float4 v = __ldg(reinterpret_cast<const float4 *>(p + i)), w = __ldg(reinterpret_cast<const float4 *>(d + i));
+                   one(v.x, w.x); one(v.y, w.y); one(v.z, w.z); one(v.w, w.w);
+               });
     block_sum2_to_double(sg, sgx, sums + 2 * c);
 }
 
 // dx = gamma*rstd*(g - mean(g) - x_hat*mean(g*x_hat));  d_gamma = sum g*x_hat, d_beta = sum g
-template <bool VEC>
-__global__ void __launch_bounds__(BNR_NT) bnr_bwd_apply_kernel(const float *__restrict__ x, const float *__restrict__ dy, int C, int HW,
+__global__ void __launch_bounds__(BNR_NT) bnr_bwd_apply_kernel(const float *__restrict__ x, const float *__restrict__ dy, int C, int HW, bool aligned,
                                                                const float *__restrict__ save, const float *__restrict__ gamma,
                                                                const float *__restrict__ beta, int relu, const double *__restrict__ sums,
                                                                double inv_count, float *__restrict__ dx, float *__restrict__ d_gamma,
                                                                float *__restrict__ d_beta) {
-    const size_t plane = blockIdx.x;
+    const size_t plane = blockIdx.x, off = plane * HW;
     const int c = (int)(plane % C);
     const float mean = save[2 * c], rstd = save[2 * c + 1], a = rstd * gamma[c], b = beta[c] - mean * a;
     const float mg = (float)(sums[2 * c] * inv_count), mgx = (float)(sums[2 * c + 1] * inv_count);
     if (plane < (size_t)C && threadIdx.x == 0) { d_beta[c] = (float)sums[2 * c]; d_gamma[c] = (float)sums[2 * c + 1]; }
-    const float *p = x + plane * HW, *d = dy + plane * HW;
-    float *q = dx + plane * HW;
+    const float *p = x + off, *d = dy + off;
+    float *q = dx + off;
     auto one = [&](float xv, float dv) {
         const float g = (!relu || fmaf(xv, a, b) > 0.f) ? dv : 0.f;
         return a * (g - mg - ((xv - mean) * rstd) * mgx);
     };
-    if (VEC) {
-        const float4 *p4 = reinterpret_cast<const float4 *>(p), *d4 = reinterpret_cast<const float4 *>(d);
-        float4 *q4 = reinterpret_cast<float4 *>(q);
-        for (int i = threadIdx.x; i < HW / 4; i += BNR_NT) {
-            const float4 v = __ldcs(p4 + i), w = __ldcs(d4 + i);
-            __stcs(q4 + i, make_float4(one(v.x, w.x), one(v.y, w.y), one(v.z, w.z), one(v.w, w.w)));
-        }
-    } else {
-        for (int i = threadIdx.x; i < HW; i += BNR_NT) q[i] = one(__ldcs(p + i), __ldcs(d + i));
+    plane_loop(HW, off, aligned,
+               [&](int i) { q[i] = one(__ldcs(p + i), __ldcs(d + i)); },
+               [&](int i) {
+                   const float4 v = __ldcs(reinterpret_cast<const float4 *>(p + i)), w = __ldcs(reinterpret_cast<const float4 *>(d + i));
+                   __stcs(reinterpret_cast<float4 *>(q + i), make_float4(one(v.x, w.x), one(v.y, w.y), one(v.z, w.z), one(v.w, w.w)));
+               });
+}
+
+// ---- nn.MaxPool2d backward on NCHW -------------------------------------------------------------------------------
+// torch's max_pool_backward_nchw is the next largest streaming cost of the step (3.2 ms for the five pools at batch 32).  With the
+// forward's argmax indices (flat h*W + w per output, what F.max_pool2d(..., return_indices=True) returns) the gradient is a
+// gather: an input pixel sums dy of the <= ceil(k/s)^2 windows that contain it and picked it.  One thread per input pixel,
+// coalesced stores, no atomics.
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float *__restrict__ dy, const long long *__restrict__ idx, int H, int W,
+                                                          int OH, int OW, int k, int s, int pad, float *__restrict__ dx, size_t total) {
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+        const size_t plane = e / ((size_t)H * W);
+        const int rem = (int)(e - plane * H * W), y = rem / W, x = rem - y * W;
+        const int oy0 = max(0, (y + pad - k + s) / s), oy1 = min(OH - 1, (y + pad) / s);      // ceil((y + pad - k + 1) / s) for non-negative numerators
+        const int ox0 = max(0, (x + pad - k + s) / s), ox1 = min(OW - 1, (x + pad) / s);
+        const float *d = dy + plane * OH * OW;
+        const long long *ix = idx + plane * OH * OW;
+        float g = 0.f;
+        for (int oy = (y + pad - k + 1 > 0 ? oy0 : 0); oy <= oy1; ++oy)
+            for (int ox = (x + pad - k + 1 > 0 ? ox0 : 0); ox <= ox1; ++ox)
+                if (__ldg(ix + oy * OW + ox) == (long long)rem) g += __ldg(d + oy * OW + ox);
+        __stcs(dx + e, g);
     }
 }
 
@@ -161,8 +176,8 @@ static int bnr_check(int N, int C, int HW) {
     if ((long)N * C > 2147483647l) return GSSD_ERR_LIMIT;
     return GSSD_OK;
 }
-static bool bnr_vec(int HW, const void *a, const void *b, const void *c) {
-    return (HW & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
+static bool bnr_aligned(const void *a, const void *b, const void *c) {          // the tensors' bases (planes are handled by plane_loop)
+    return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
 }
 
 }  // namespace gssd
@@ -180,17 +195,11 @@ extern "C" int gssd_bn_relu_nchw_fwd(const float *x, const float *gamma, const f
     GSSD_RETURN_IF_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
     const double count = (double)N * HW, unbias = count > 1 ? count / (count - 1) : 1.0;
     const unsigned planes = (unsigned)((long)N * C);
-    if (bnr_vec(HW, x, y, x)) {
-        bnr_stats_kernel<true><<<planes, BNR_NT, 0, st>>>(x, C, HW, ws);
-        GSSD_AFTER_LAUNCH();
-        bnr_apply_kernel<true><<<planes, BNR_NT, 0, st>>>(x, C, HW, ws, 1.0 / count, unbias, eps, gamma, beta, relu, y, save_mean_rstd,
-                                                          running_mean, running_var, momentum);
-    } else {
-        bnr_stats_kernel<false><<<planes, BNR_NT, 0, st>>>(x, C, HW, ws);
-        GSSD_AFTER_LAUNCH();
-        bnr_apply_kernel<false><<<planes, BNR_NT, 0, st>>>(x, C, HW, ws, 1.0 / count, unbias, eps, gamma, beta, relu, y, save_mean_rstd,
-                                                           running_mean, running_var, momentum);
-    }
+    const bool al = bnr_aligned(x, y, x);
+    bnr_stats_kernel<<<planes, BNR_NT, 0, st>>>(x, C, HW, al, ws);
+    GSSD_AFTER_LAUNCH();
+    bnr_apply_kernel<<<planes, BNR_NT, 0, st>>>(x, C, HW, al, ws, 1.0 / count, unbias, eps, gamma, beta, relu, y, save_mean_rstd, running_mean,
+                                                running_var, momentum);
     GSSD_AFTER_LAUNCH();
     return GSSD_OK;
 }
@@ -204,15 +213,26 @@ extern "C" int gssd_bn_relu_nchw_bwd(const float *x, const float *dy, const floa
     GSSD_RETURN_IF_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
     const double count = (double)N * HW;
     const unsigned planes = (unsigned)((long)N * C);
-    if (bnr_vec(HW, x, dy, dx)) {
-        bnr_bwd_reduce_kernel<true><<<planes, BNR_NT, 0, st>>>(x, dy, C, HW, save_mean_rstd, gamma, beta, relu, ws);
-        GSSD_AFTER_LAUNCH();
-        bnr_bwd_apply_kernel<true><<<planes, BNR_NT, 0, st>>>(x, dy, C, HW, save_mean_rstd, gamma, beta, relu, ws, 1.0 / count, dx, d_gamma, d_beta);
-    } else {
-        bnr_bwd_reduce_kernel<false><<<planes, BNR_NT, 0, st>>>(x, dy, C, HW, save_mean_rstd, gamma, beta, relu, ws);
-        GSSD_AFTER_LAUNCH();
-        bnr_bwd_apply_kernel<false><<<planes, BNR_NT, 0, st>>>(x, dy, C, HW, save_mean_rstd, gamma, beta, relu, ws, 1.0 / count, dx, d_gamma, d_beta);
-    }
+    const bool al = bnr_aligned(x, dy, dx);
+    bnr_bwd_reduce_kernel<<<planes, BNR_NT, 0, st>>>(x, dy, C, HW, al, save_mean_rstd, gamma, beta, relu, ws);
+    GSSD_AFTER_LAUNCH();
+    bnr_bwd_apply_kernel<<<planes, BNR_NT, 0, st>>>(x, dy, C, HW, al, save_mean_rstd, gamma, beta, relu, ws, 1.0 / count, dx, d_gamma, d_beta);
+    GSSD_AFTER_LAUNCH();
+    return GSSD_OK;
+}
+
+extern "C" int gssd_maxpool_nchw_bwd(const float *dy, const int64_t *indices, int planes, int H, int W, int OH, int OW, int kernel, int stride,
+                                     int pad, float *dx, void *stream) {
+    if (!dy || !indices || !dx) return GSSD_ERR_ARG;
+    if (planes <= 0 || H <= 0 || W <= 0 || OH <= 0 || OW <= 0 || kernel <= 0 || stride <= 0 || pad < 0 || 2 * pad > kernel) return GSSD_ERR_ARG;
+    const size_t total = (size_t)planes * H * W;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t want = (total + 255) / 256;
+    const unsigned grid = (unsigned)(want < (size_t)sms * 32 ? want : (size_t)sms * 32);
+    maxpool_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, reinterpret_cast<const long long *>(indices), H, W, OH, OW, kernel, stride, pad,
+                                                              dx, total);
     GSSD_AFTER_LAUNCH();
     return GSSD_OK;
 }

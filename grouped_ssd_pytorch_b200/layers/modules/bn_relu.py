@@ -68,9 +68,53 @@ def bn_relu(x, bn, relu=True):
     return y
 
 
+class _MaxPoolNCHW(torch.autograd.Function):
+    """nn.MaxPool2d whose backward is the gather kernel `gssd_maxpool_nchw_bwd` (forward: torch's own kernel with indices)."""
+
+    @staticmethod
+    def forward(ctx, x, k, s, pad, ceil_mode):
+        y, idx = torch.nn.functional.max_pool2d(x, k, s, pad, 1, ceil_mode, return_indices=True)
+        ctx.save_for_backward(idx)
+        ctx.geom = (x.shape, k, s, pad)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        lib = _lib.require_cuda()
+        (idx,) = ctx.saved_tensors
+        shape, k, s, pad = ctx.geom
+        dev = idx.device
+        dyc = _lib.f32(dy, dev)
+        dx = torch.empty(shape, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.gssd_maxpool_nchw_bwd(dyc.data_ptr(), idx.data_ptr(), shape[0] * shape[1], shape[2], shape[3], idx.shape[2],
+                                                 idx.shape[3], k, s, pad, dx.data_ptr(), _lib.stream()), "gssd_maxpool_nchw_bwd")
+        return dx, None, None, None, None
+
+
+def _pool_geometry(m):
+    """(kernel, stride, padding) of a square, undilated nn.MaxPool2d, else None"""
+    def one(v):
+        v = tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+        return v[0] if v[0] == v[1] else None
+    k, s, p, d = one(m.kernel_size), one(m.stride if m.stride is not None else m.kernel_size), one(m.padding), one(m.dilation)
+    return None if None in (k, s, p) or d != 1 or m.return_indices else (int(k), int(s), int(p))
+
+
+def max_pool(x, m):
+    """m(x) for an nn.MaxPool2d `m`, with the gather backward when a gradient will flow (CUDA fp32 NCHW), else the module itself"""
+    geom = _pool_geometry(m) if isinstance(m, nn.MaxPool2d) else None
+    if (geom is None or not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4)
+            or not (torch.is_grad_enabled() and x.requires_grad)):
+        return m(x)
+    return _MaxPoolNCHW.apply(x.contiguous(), geom[0], geom[1], geom[2], bool(m.ceil_mode))
+
+
 def run_layers(modules, x, start=0, stop=None):
     """x through modules[start:stop]; every training-mode (BatchNorm2d, ReLU) pair runs as one fused node, a BatchNorm2d without a
-    ReLU behind it as the same kernels without the clamp, everything else as the module itself."""
+    ReLU behind it as the same kernels without the clamp, an nn.MaxPool2d with the gather backward, everything else as the module
+    itself."""
     stop = len(modules) if stop is None else stop
     k = start
     while k < stop:
@@ -79,6 +123,9 @@ def run_layers(modules, x, start=0, stop=None):
             fuse = k + 1 < stop and isinstance(modules[k + 1], nn.ReLU)
             x = bn_relu(x, m, relu=fuse)
             k += 2 if fuse else 1
+        elif isinstance(m, nn.MaxPool2d):
+            x = max_pool(x, m)
+            k += 1
         else:
             x = m(x)
             k += 1

@@ -371,6 +371,12 @@ GSSD_API int gssd_bn_relu_nchw_fwd(const float *x, const float *gamma, const flo
 GSSD_API int gssd_bn_relu_nchw_bwd(const float *x, const float *dy, const float *gamma, const float *beta, const float *save_mean_rstd,
                           int N, int C, int HW, int relu, float *dx, float *d_gamma, float *d_beta, double *ws, void *stream);
 
+/* nn.MaxPool2d backward on NCHW fp32 (the pools between the grouped backbone convolutions, ssd_multiphase_custom_group.py:437-446;
+ * dilation 1): indices[planes, OH, OW] int64 = flat h*W + w of every window's maximum, as F.max_pool2d(..., return_indices=True)
+ * returns them; dx[planes, H, W] is written completely (a gather, no atomics). */
+GSSD_API int gssd_maxpool_nchw_bwd(const float *dy, const int64_t *indices, int planes, int H, int W, int OH, int OW, int kernel, int stride,
+                          int pad, float *dx, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Modulated deformable convolution (DCNv2) of GSSD++ — replaces `dcn_v2._DCNv2.apply` as called at
  * layers/dcn_v2_custom.py:49-55 and 84-88 (3x3, stride 1, padding 1, dilation 1).

@@ -10,7 +10,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from grouped_ssd_pytorch_b200 import _lib
-from grouped_ssd_pytorch_b200.layers.modules.bn_relu import bn_relu, run_layers, takes
+from grouped_ssd_pytorch_b200.layers.modules.bn_relu import bn_relu, max_pool, run_layers, takes
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -70,7 +70,7 @@ def test_run_layers_fuses_pairs_and_leaves_the_rest():
     n0 = _lib.launch_count()
     y = run_layers(mods, x)
     y.square().sum().backward()
-    assert _lib.launch_count() == n0 + 8                                    # two fused pairs
+    assert _lib.launch_count() == n0 + 9                                    # two fused pairs + the pool's backward
     gx, x.grad = x.grad, None
     yr = ref(x)
     yr.square().sum().backward()
@@ -119,3 +119,22 @@ def test_bn_relu_bandwidth_at_the_backbone_size():
     gb = x.numel() * 4 * 8 / 1e9                                            # 3 passes forward, 5 backward
     print("BN + ReLU forward + backward at [32, 64, 300, 300]: ours %.2f ms (%.0f GB/s of the 8 algorithmic passes), torch / cuDNN %.2f ms" % (t_o, gb / t_o * 1e3, t_r))
     assert t_o < t_r
+
+
+@pytest.mark.parametrize("shape,k,s,p,ceil", [((2, 8, 30, 30), 2, 2, 0, False), ((2, 4, 75, 75), 2, 2, 0, True), ((3, 6, 19, 19), 3, 1, 1, False),
+                                               ((1, 5, 10, 11), 3, 2, 1, True), ((2, 3, 7, 7), 3, 3, 0, False), ((4, 64, 150, 150), 2, 2, 0, False)])
+def test_max_pool_backward_is_torchs(shape, k, s, p, ceil):
+    """the pools of the backbone (ssd_multiphase_custom_group.py:437-446: 2x2/2, 2x2/2 ceil_mode, 3x3/1 pad 1) and a few others; ReLU-like
+    inputs with many exact ties (zeros): the argmax is torch's own (the forward is its kernel), the gradient must be bit-equal"""
+    torch.manual_seed(k * 10 + s)
+    x = torch.relu(torch.randn(shape, device=DEV)).requires_grad_(True)
+    m = nn.MaxPool2d(k, s, p, ceil_mode=ceil)
+    gout = torch.randn(m(x).shape, device=DEV)
+    n0 = _lib.launch_count()
+    max_pool(x, m).backward(gout)
+    assert _lib.launch_count() == n0 + 1
+    gx, x.grad = x.grad, None
+    m(x).backward(gout)
+    assert torch.equal(gx, x.grad) or float((gx - x.grad).abs().max()) <= 1e-6 * float(x.grad.abs().max())    # (overlapping windows: summation order)
+    with torch.no_grad():
+        assert torch.equal(max_pool(x.detach(), m), m(x.detach()))
