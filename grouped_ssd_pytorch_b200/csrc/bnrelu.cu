@@ -152,23 +152,55 @@ __global__ void __launch_bounds__(BNR_NT) bnr_bwd_apply_kernel(const float *__re
 // ---- nn.MaxPool2d backward on NCHW -------------------------------------------------------------------------------
 // torch's max_pool_backward_nchw is the next largest streaming cost of the step (3.2 ms for the five pools at batch 32).  With the
 // forward's argmax indices (flat h*W + w per output, what F.max_pool2d(..., return_indices=True) returns) the gradient is a
-// gather: an input pixel sums dy of the <= ceil(k/s)^2 windows that contain it and picked it.  One thread per input pixel,
-// coalesced stores, no atomics.
-__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float *__restrict__ dy, const long long *__restrict__ idx, int H, int W,
-                                                          int OH, int OW, int k, int s, int pad, float *__restrict__ dx, size_t total) {
-    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
-        const size_t plane = e / ((size_t)H * W);
-        const int rem = (int)(e - plane * H * W), y = rem / W, x = rem - y * W;
-        const int oy0 = max(0, (y + pad - k + s) / s), oy1 = min(OH - 1, (y + pad) / s);      // ceil((y + pad - k + 1) / s) for non-negative numerators
-        const int ox0 = max(0, (x + pad - k + s) / s), ox1 = min(OW - 1, (x + pad) / s);
-        const float *d = dy + plane * OH * OW;
-        const long long *ix = idx + plane * OH * OW;
-        float g = 0.f;
-        for (int oy = (y + pad - k + 1 > 0 ? oy0 : 0); oy <= oy1; ++oy)
-            for (int ox = (x + pad - k + 1 > 0 ? ox0 : 0); ox <= ox1; ++ox)
-                if (__ldg(ix + oy * OW + ox) == (long long)rem) g += __ldg(d + oy * OW + ox);
-        __stcs(dx + e, g);
+// scatter without collisions for the 2x2 / stride 2 pools — one thread per window writes its four input pixels, 8-byte stores
+// along the row — and a gather for overlapping windows (3x3 / stride 1): an input pixel sums dy of the <= ceil(k/s)^2 windows
+// that contain it and picked it.  No atomics, dx written exactly once.  (A first, gather-only version with 64-bit index
+// arithmetic per element took 2.6 ms for the five pools.)
+template <bool EVEN_W>
+__global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const float *__restrict__ dy, const long long *__restrict__ idx, int H, int W,
+                                                             int OH, int OW, float *__restrict__ dx) {
+    const int o = blockIdx.x * 256 + threadIdx.x;
+    if (o >= OH * OW) return;
+    const size_t plane = blockIdx.y;
+    const int oy = o / OW, ox = o - oy * OW, y0 = 2 * oy, x0 = 2 * ox;
+    const float g = __ldg(dy + plane * OH * OW + o);
+    const int t = (int)(__ldg(idx + plane * OH * OW + o) - ((long long)y0 * W + x0));       // 0, 1, W or W + 1
+    float *q = dx + plane * H * W + (size_t)y0 * W + x0;
+    const bool row1 = y0 + 1 < H, col1 = x0 + 1 < W;                                           // ceil_mode windows may hang over the edge
+    if (EVEN_W) {
+        __stcs(reinterpret_cast<float2 *>(q), make_float2(t == 0 ? g : 0.f, t == 1 ? g : 0.f));
+        if (row1) __stcs(reinterpret_cast<float2 *>(q + W), make_float2(t == W ? g : 0.f, t == W + 1 ? g : 0.f));
+    } else {
+        q[0] = t == 0 ? g : 0.f;
+        if (col1) q[1] = t == 1 ? g : 0.f;
+        if (row1) { q[W] = t == W ? g : 0.f; if (col1) q[W + 1] = t == W + 1 ? g : 0.f; }
     }
+    // pixels no window covers (floor mode on odd extents) have no gradient
+    if (ox == OW - 1)
+        for (int x = 2 * OW; x < W; ++x) { dx[plane * H * W + (size_t)y0 * W + x] = 0.f; if (row1) dx[plane * H * W + (size_t)(y0 + 1) * W + x] = 0.f; }
+    if (oy == OH - 1)
+        for (int y = 2 * OH; y < H; ++y) {
+            float *r = dx + plane * H * W + (size_t)y * W;
+            r[x0] = 0.f; if (col1) r[x0 + 1] = 0.f;
+            if (ox == OW - 1) for (int x = 2 * OW; x < W; ++x) r[x] = 0.f;
+        }
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float *__restrict__ dy, const long long *__restrict__ idx, int H, int W,
+                                                          int OH, int OW, int k, int s, int pad, float *__restrict__ dx) {
+    const int rem = blockIdx.x * 256 + threadIdx.x;
+    if (rem >= H * W) return;
+    const size_t plane = blockIdx.y;
+    const int y = rem / W, x = rem - y * W;
+    const int oy0 = y + pad - k + 1 > 0 ? (y + pad - k + s) / s : 0, oy1 = min(OH - 1, (y + pad) / s);      // ceil((y + pad - k + 1) / s) .. floor((y + pad) / s)
+    const int ox0 = x + pad - k + 1 > 0 ? (x + pad - k + s) / s : 0, ox1 = min(OW - 1, (x + pad) / s);
+    const float *d = dy + plane * OH * OW;
+    const long long *ix = idx + plane * OH * OW;
+    float g = 0.f;
+    for (int oy = oy0; oy <= oy1; ++oy)
+        for (int ox = ox0; ox <= ox1; ++ox)
+            if (__ldg(ix + oy * OW + ox) == (long long)rem) g += __ldg(d + oy * OW + ox);
+    __stcs(dx + plane * H * W + rem, g);
 }
 
 static int bnr_check(int N, int C, int HW) {
@@ -225,14 +257,23 @@ extern "C" int gssd_maxpool_nchw_bwd(const float *dy, const int64_t *indices, in
                                      int pad, float *dx, void *stream) {
     if (!dy || !indices || !dx) return GSSD_ERR_ARG;
     if (planes <= 0 || H <= 0 || W <= 0 || OH <= 0 || OW <= 0 || kernel <= 0 || stride <= 0 || pad < 0 || 2 * pad > kernel) return GSSD_ERR_ARG;
-    const size_t total = (size_t)planes * H * W;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t want = (total + 255) / 256;
-    const unsigned grid = (unsigned)(want < (size_t)sms * 32 ? want : (size_t)sms * 32);
-    maxpool_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, reinterpret_cast<const long long *>(indices), H, W, OH, OW, kernel, stride, pad,
-                                                              dx, total);
-    GSSD_AFTER_LAUNCH();
+    if (planes > 65535 * 32) return GSSD_ERR_LIMIT;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long *ix = reinterpret_cast<const long long *>(indices);
+    // gridDim.y is limited to 65535: planes beyond that go into further launches
+    for (int p0 = 0; p0 < planes; p0 += 65535) {
+        const int np = planes - p0 < 65535 ? planes - p0 : 65535;
+        const float *dyp = dy + (size_t)p0 * OH * OW;
+        const long long *ixp = ix + (size_t)p0 * OH * OW;
+        float *dxp = dx + (size_t)p0 * H * W;
+        if (kernel == 2 && stride == 2 && pad == 0) {
+            const dim3 grid((OH * OW + 255) / 256, np);
+            if ((W & 1) == 0 && (reinterpret_cast<uintptr_t>(dxp) & 7) == 0) maxpool2x2_bwd_kernel<true><<<grid, 256, 0, st>>>(dyp, ixp, H, W, OH, OW, dxp);
+            else maxpool2x2_bwd_kernel<false><<<grid, 256, 0, st>>>(dyp, ixp, H, W, OH, OW, dxp);
+        } else {
+            maxpool_bwd_kernel<<<dim3((H * W + 255) / 256, np), 256, 0, st>>>(dyp, ixp, H, W, OH, OW, kernel, stride, pad, dxp);
+        }
+        GSSD_AFTER_LAUNCH();
+    }
     return GSSD_OK;
 }
