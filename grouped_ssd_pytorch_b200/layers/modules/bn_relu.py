@@ -13,24 +13,39 @@ import torch.nn as nn
 from ... import _lib
 
 
+def _is_channels_last(x):
+    """a genuinely channels-last 4-D tensor (not one that is contiguous in both senses, e.g. 1x1 maps or one channel)"""
+    return x.dim() == 4 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last)
+
+
+def _nhwc_ok(c):
+    return c % 4 == 0 and c <= 1024 and 256 % (c // 4) == 0
+
+
 class _BnReluTrain(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, relu):
         lib = _lib.require_cuda()
         dev = x.device
-        xc = x.contiguous()
+        cl = _is_channels_last(x) and _nhwc_ok(x.shape[1])
+        xc = x if cl else x.contiguous()
         N, C = xc.shape[0], xc.shape[1]
         HW = xc.numel() // (N * C)
-        y = torch.empty_like(xc)
+        y = torch.empty_like(xc)                                  # keeps the memory format
         save = torch.empty((2 * C,), dtype=torch.float32, device=dev)
         ws = torch.empty((2 * C,), dtype=torch.float64, device=dev)
         w, b = _lib.f32(weight, dev), _lib.f32(bias, dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.gssd_bn_relu_nchw_fwd(xc.data_ptr(), w.data_ptr(), b.data_ptr(), N, C, HW, float(eps), 1 if relu else 0,
-                                                 y.data_ptr(), save.data_ptr(), _lib.ptr(running_mean), _lib.ptr(running_var),
-                                                 float(momentum), ws.data_ptr(), _lib.stream()), "gssd_bn_relu_nchw_fwd")
+            if cl:
+                _lib.check(lib.gssd_bn_relu_nhwc_fwd(xc.data_ptr(), w.data_ptr(), b.data_ptr(), N * HW, C, float(eps), 1 if relu else 0,
+                                                     y.data_ptr(), save.data_ptr(), _lib.ptr(running_mean), _lib.ptr(running_var),
+                                                     float(momentum), ws.data_ptr(), _lib.stream()), "gssd_bn_relu_nhwc_fwd")
+            else:
+                _lib.check(lib.gssd_bn_relu_nchw_fwd(xc.data_ptr(), w.data_ptr(), b.data_ptr(), N, C, HW, float(eps), 1 if relu else 0,
+                                                     y.data_ptr(), save.data_ptr(), _lib.ptr(running_mean), _lib.ptr(running_var),
+                                                     float(momentum), ws.data_ptr(), _lib.stream()), "gssd_bn_relu_nchw_fwd")
         ctx.save_for_backward(xc, w, b, save)
-        ctx.relu = relu
+        ctx.relu, ctx.cl = relu, cl
         return y
 
     @staticmethod
@@ -41,14 +56,20 @@ class _BnReluTrain(torch.autograd.Function):
         dev = xc.device
         N, C = xc.shape[0], xc.shape[1]
         HW = xc.numel() // (N * C)
-        dyc = _lib.f32(dy, dev)
+        dyc = dy.detach().to(device=dev, dtype=torch.float32)
+        dyc = dyc.contiguous(memory_format=torch.channels_last) if ctx.cl else dyc.contiguous()
         dx = torch.empty_like(xc)
         dg, db = torch.empty_like(w), torch.empty_like(b)
         ws = torch.empty((2 * C,), dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.gssd_bn_relu_nchw_bwd(xc.data_ptr(), dyc.data_ptr(), w.data_ptr(), b.data_ptr(), save.data_ptr(), N, C, HW,
-                                                 1 if ctx.relu else 0, dx.data_ptr(), dg.data_ptr(), db.data_ptr(), ws.data_ptr(),
-                                                 _lib.stream()), "gssd_bn_relu_nchw_bwd")
+            if ctx.cl:
+                _lib.check(lib.gssd_bn_relu_nhwc_bwd(xc.data_ptr(), dyc.data_ptr(), w.data_ptr(), b.data_ptr(), save.data_ptr(), N * HW, C,
+                                                     1 if ctx.relu else 0, dx.data_ptr(), dg.data_ptr(), db.data_ptr(), ws.data_ptr(),
+                                                     _lib.stream()), "gssd_bn_relu_nhwc_bwd")
+            else:
+                _lib.check(lib.gssd_bn_relu_nchw_bwd(xc.data_ptr(), dyc.data_ptr(), w.data_ptr(), b.data_ptr(), save.data_ptr(), N, C, HW,
+                                                     1 if ctx.relu else 0, dx.data_ptr(), dg.data_ptr(), db.data_ptr(), ws.data_ptr(),
+                                                     _lib.stream()), "gssd_bn_relu_nchw_bwd")
         return dx, dg, db, None, None, None, None, None
 
 
@@ -69,13 +90,15 @@ def bn_relu(x, bn, relu=True):
 
 
 class _MaxPoolNCHW(torch.autograd.Function):
-    """nn.MaxPool2d whose backward is the gather kernel `gssd_maxpool_nchw_bwd` (forward: torch's own kernel with indices)."""
+    """nn.MaxPool2d whose backward is `gssd_maxpool_nchw_bwd` / `gssd_maxpool_nhwc_bwd` (forward: torch's own kernel with indices)."""
 
     @staticmethod
     def forward(ctx, x, k, s, pad, ceil_mode):
+        cl = _is_channels_last(x) and x.shape[1] % 4 == 0
         y, idx = torch.nn.functional.max_pool2d(x, k, s, pad, 1, ceil_mode, return_indices=True)
+        idx = idx.contiguous(memory_format=torch.channels_last) if cl else idx.contiguous()
         ctx.save_for_backward(idx)
-        ctx.geom = (x.shape, k, s, pad)
+        ctx.geom = (x.shape, k, s, pad, cl)
         return y
 
     @staticmethod
@@ -83,13 +106,20 @@ class _MaxPoolNCHW(torch.autograd.Function):
     def backward(ctx, dy):
         lib = _lib.require_cuda()
         (idx,) = ctx.saved_tensors
-        shape, k, s, pad = ctx.geom
+        shape, k, s, pad, cl = ctx.geom
         dev = idx.device
-        dyc = _lib.f32(dy, dev)
-        dx = torch.empty(shape, dtype=torch.float32, device=dev)
+        dyc = dy.detach().to(device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
-            _lib.check(lib.gssd_maxpool_nchw_bwd(dyc.data_ptr(), idx.data_ptr(), shape[0] * shape[1], shape[2], shape[3], idx.shape[2],
-                                                 idx.shape[3], k, s, pad, dx.data_ptr(), _lib.stream()), "gssd_maxpool_nchw_bwd")
+            if cl:
+                dyc = dyc.contiguous(memory_format=torch.channels_last)
+                dx = torch.empty(shape, dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+                _lib.check(lib.gssd_maxpool_nhwc_bwd(dyc.data_ptr(), idx.data_ptr(), shape[0], shape[1], shape[2], shape[3], idx.shape[2],
+                                                     idx.shape[3], k, s, pad, dx.data_ptr(), _lib.stream()), "gssd_maxpool_nhwc_bwd")
+            else:
+                dyc = dyc.contiguous()
+                dx = torch.empty(shape, dtype=torch.float32, device=dev)
+                _lib.check(lib.gssd_maxpool_nchw_bwd(dyc.data_ptr(), idx.data_ptr(), shape[0] * shape[1], shape[2], shape[3], idx.shape[2],
+                                                     idx.shape[3], k, s, pad, dx.data_ptr(), _lib.stream()), "gssd_maxpool_nchw_bwd")
         return dx, None, None, None, None
 
 
@@ -108,7 +138,17 @@ def max_pool(x, m):
     if (geom is None or not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4)
             or not (torch.is_grad_enabled() and x.requires_grad)):
         return m(x)
-    return _MaxPoolNCHW.apply(x.contiguous(), geom[0], geom[1], geom[2], bool(m.ceil_mode))
+    xin = x if _is_channels_last(x) and x.shape[1] % 4 == 0 else x.contiguous()
+    return _MaxPoolNCHW.apply(xin, geom[0], geom[1], geom[2], bool(m.ceil_mode))
+
+
+def to_channels_last(modules):
+    """store the filters of every nn.Conv2d of `modules` channels-last, once (values, names and state dict are unchanged): with a
+    channels-last input cuDNN then runs its NHWC kernels without converting the filter at every call"""
+    for m in modules:
+        if isinstance(m, nn.Conv2d) and m.weight.dim() == 4 and not _is_channels_last(m.weight) and m.weight.shape[1] > 1:
+            with torch.no_grad():
+                m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
 
 
 def run_layers(modules, x, start=0, stop=None):

@@ -596,9 +596,14 @@ def gssd_forward(net, x, detect_args=(0, 200, 0.01, 0.45), backbone=False):
     import os
     import torch.nn.functional as F
     from ..functions import Detect
-    from .bn_relu import bn_relu, run_layers, takes as bn_takes
+    from .bn_relu import bn_relu, run_layers, takes as bn_takes, to_channels_last
     _lib.require_cuda()
     fuse_bn = os.environ.get("GSSD_FUSED_BN", "1") != "0"    # development: A/B against torch's BatchNorm2d + ReLU modules
+    # opt-in (GSSD_CHANNELS_LAST=1): the torch convolutions between the source blocks run channels-last (cuDNN's NHWC kernels, no
+    # layout conversion passes), with the fused BatchNorm / ReLU / pool kernels in their channels-last form.  Measured at batch 32:
+    # 33.4 ms against 33.9 ms per training step - what cuDNN saves on conversions it loses on its NHWC grouped convolutions - so it
+    # is not the default
+    chl = fuse_bn and net.training and os.environ.get("GSSD_CHANNELS_LAST", "0") == "1"
 
     def _plain(mods, xx, a, b):
         for kk in range(a, b):
@@ -653,9 +658,16 @@ def gssd_forward(net, x, detect_args=(0, 200, 0.01, 0.45), backbone=False):
         else:
             # the backbone layers in between stay the model's torch convolutions / pools; in training mode every (BatchNorm2d, ReLU)
             # pair behind them runs as one fused node (bn_relu.py: the largest cost of the reference's training step)
+            if chl:
+                if not getattr(net, "_gssd_channels_last", False):
+                    to_channels_last(net.vgg)
+                    net._gssd_channels_last = True
+                x = x.contiguous(memory_format=torch.channels_last)
             x = run_layers(net.vgg, x, 0, i43) if fuse_bn else _plain(net.vgg, x, 0, i43)      # GSSD:254-259, up to the input of conv4_3
             x1 = run_block(blocks[0], x)                         # conv4_3 .. heads of source 1 (GSSD:258-297, 375-377)
             x = x1 if use_ag else x1.to_nchw()                   # post-ReLU conv4_3 continues down the backbone
+            if chl:
+                x = x.contiguous(memory_format=torch.channels_last)
             k0 = i43 + (3 if bn else 2)                          # GSSD:300-301 up to the input of conv7
             x = run_layers(net.vgg, x, k0, i7) if fuse_bn else _plain(net.vgg, x, k0, i7)
             x2 = run_block(blocks[1], x)                         # conv7 .. heads of source 2 (GSSD:300-325)

@@ -377,6 +377,15 @@ GSSD_API int gssd_bn_relu_nchw_bwd(const float *x, const float *dy, const float 
 GSSD_API int gssd_maxpool_nchw_bwd(const float *dy, const int64_t *indices, int planes, int H, int W, int OH, int OW, int kernel, int stride,
                           int pad, float *dx, void *stream);
 
+/* The same three operators on channels-last tensors (torch.channels_last: [rows = N*H*W, C] with the channels innermost), for a
+ * backbone whose convolutions run on cuDNN's NHWC kernels.  C must be 4 times a power of two, at most 1024. */
+GSSD_API int gssd_bn_relu_nhwc_fwd(const float *x, const float *gamma, const float *beta, long rows, int C, float eps, int relu, float *y,
+                          float *save_mean_rstd, float *running_mean, float *running_var, float momentum, double *ws, void *stream);
+GSSD_API int gssd_bn_relu_nhwc_bwd(const float *x, const float *dy, const float *gamma, const float *beta, const float *save_mean_rstd,
+                          long rows, int C, int relu, float *dx, float *d_gamma, float *d_beta, double *ws, void *stream);
+GSSD_API int gssd_maxpool_nhwc_bwd(const float *dy, const int64_t *indices, int N, int C, int H, int W, int OH, int OW, int kernel, int stride,
+                          int pad, float *dx, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Modulated deformable convolution (DCNv2) of GSSD++ — replaces `dcn_v2._DCNv2.apply` as called at
  * layers/dcn_v2_custom.py:49-55 and 84-88 (3x3, stride 1, padding 1, dilation 1).

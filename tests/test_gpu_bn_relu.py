@@ -138,3 +138,44 @@ def test_max_pool_backward_is_torchs(shape, k, s, p, ceil):
     assert torch.equal(gx, x.grad) or float((gx - x.grad).abs().max()) <= 1e-6 * float(x.grad.abs().max())    # (overlapping windows: summation order)
     with torch.no_grad():
         assert torch.equal(max_pool(x.detach(), m), m(x.detach()))
+
+
+@pytest.mark.parametrize("shape,relu", [((4, 16, 30, 30), True), ((2, 64, 5, 7), True), ((2, 12, 19, 19), False), ((3, 1024, 3, 3), True),
+                                         ((8, 64, 150, 150), True)])
+def test_bn_relu_channels_last_vs_torch(shape, relu):
+    """the channels-last form (gssd_bn_relu_nhwc_*): same numbers, output and input gradient stay channels-last"""
+    torch.manual_seed(sum(shape) + 1)
+    N, C, H, W = shape
+    x = (torch.randn(shape, device=DEV) * 1.3 - 0.2).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    bn_a, bn_b = nn.BatchNorm2d(C).to(DEV).train(), nn.BatchNorm2d(C).to(DEV).train()
+    with torch.no_grad():
+        bn_a.weight.uniform_(0.5, 1.5); bn_a.bias.normal_(0, 0.3)
+    bn_b.load_state_dict(bn_a.state_dict())
+    gout = torch.randn(shape, device=DEV).contiguous(memory_format=torch.channels_last)
+    y = bn_relu(x, bn_a, relu=relu)
+    nhwc = C % 4 == 0 and 256 % (C // 4) == 0                          # else the NCHW kernels serve a contiguous copy
+    assert y.is_contiguous(memory_format=torch.channels_last) == nhwc or (H == 1 and W == 1)
+    y.backward(gout)
+    gx, x.grad = x.grad, None
+    yr = bn_b(x)
+    yr = F.relu(yr) if relu else yr
+    yr.backward(gout)
+    errs = dict(y=rel(y, yr), dx=rel(gx, x.grad), dw=rel(bn_a.weight.grad, bn_b.weight.grad), db=rel(bn_a.bias.grad, bn_b.bias.grad),
+                rm=rel(bn_a.running_mean, bn_b.running_mean), rv=rel(bn_a.running_var, bn_b.running_var))
+    print(shape, relu, {k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) <= 2e-5, errs
+
+
+@pytest.mark.parametrize("shape,k,s,p,ceil", [((2, 8, 30, 30), 2, 2, 0, False), ((2, 4, 75, 75), 2, 2, 0, True), ((3, 8, 19, 19), 3, 1, 1, False),
+                                               ((1, 12, 10, 11), 3, 2, 1, True), ((2, 16, 7, 7), 2, 2, 0, False), ((4, 64, 150, 150), 2, 2, 0, False)])
+def test_max_pool_backward_channels_last(shape, k, s, p, ceil):
+    torch.manual_seed(k * 10 + s + 1)
+    x = torch.relu(torch.randn(shape, device=DEV)).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    m = nn.MaxPool2d(k, s, p, ceil_mode=ceil)
+    gout = torch.randn(m(x).shape, device=DEV).contiguous(memory_format=torch.channels_last)
+    out = max_pool(x, m)
+    out.backward(gout)
+    gx, x.grad = x.grad, None
+    assert gx.is_contiguous(memory_format=torch.channels_last)
+    m(x).backward(gout)
+    assert torch.equal(gx, x.grad) or float((gx - x.grad).abs().max()) <= 1e-6 * float(x.grad.abs().max())
