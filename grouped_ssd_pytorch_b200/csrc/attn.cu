@@ -20,6 +20,9 @@ constexpr int AT_NT = 256;
 constexpr int AT_DC = 64;            // contraction chunk of strip_gemm
 constexpr int AT_KA = 128;           // keys per tile of strip_gemm (16 per warp)
 constexpr int AT_TAP = AT_KA + 8;    // its row pitch: 8 mod 32, so the A fragments (4 rows x 8 columns per load) hit 32 banks
+// row pitch of the query tile: 8 mod 32 (B fragments: 4 rows x 8 columns per load on 32 banks; QT + 8 made it 32 at 24 queries:
+// 4-way conflicts, 22 % of the backward's samples on that load)
+__host__ __device__ constexpr int at_qsp(int qt) { return (qt - 8 + 31) / 32 * 32 + 8; }
 constexpr int AT_KC = 64;            // keys per tile of strip_apply: few, large tiles — with 16 keys per tile every one of the 91 steps
                                      // of a 1444-key strip exposed an L2 round trip (ncu: 44 % of the samples on the tile loads)
 
@@ -39,13 +42,13 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], flo
 }
 
 // strip[q][m] (+)= sum_{d < Dn} A[d*lda + q0 + q] * Bm[d*ldb + m]     for q < QT (zero rows beyond nq), m < L
-// qs: [AT_DC][QT + 8] floats, tile: [AT_DC][AT_TAP] floats.  MMA roles: M = 16 keys (one m-tile per warp and key tile), N = 8
+// qs: [AT_DC][at_qsp(QT)] floats, tile: [AT_DC][AT_TAP] floats.  MMA roles: M = 16 keys (one m-tile per warp and key tile), N = 8
 // queries, K = 8 of the contraction.  Every (q, m) of the strip belongs to one thread, so the read-modify-write over the chunks
 // of the contraction needs no synchronisation of its own.
 template <int QT>
 __device__ __forceinline__ void strip_gemm(float *strip, int Lp, int L, const float *__restrict__ A, int lda, int q0, int nq,
                                            const float *__restrict__ Bm, int ldb, int Dn, float *qs, float *tile) {
-    constexpr int NT = QT / 8, QSP = QT + 8, TPT = AT_DC * AT_KA / AT_NT;
+    constexpr int NT = QT / 8, QSP = at_qsp(QT), TPT = AT_DC * AT_KA / AT_NT;
     static_assert(TPT % 4 == 0, "tile shape");
     const int tid = threadIdx.x, warp = tid >> 5, grp = (tid & 31) >> 2, tig = tid & 3;
     const bool vec = (ldb & 3) == 0 && (reinterpret_cast<uintptr_t>(Bm) & 15) == 0;
@@ -220,7 +223,7 @@ static size_t attn_smem_floats(int QT, int L, int D) {
     size_t tile = (size_t)AT_DC * AT_TAP;
     if ((size_t)256 * (AT_KC + 4) > tile) tile = (size_t)256 * (AT_KC + 4);
     (void)D;
-    return (size_t)QT * Lp + 16 + (size_t)AT_DC * (QT + 8) + tile;      // + 16: reads past the last row's end stay inside
+    return (size_t)QT * Lp + 16 + (size_t)AT_DC * at_qsp(QT) + tile;      // + 16: reads past the last row's end stay inside
 }
 
 // forward: scores -> softmax (attn written once) -> attn_g
@@ -228,7 +231,7 @@ template <int QT>
 __global__ void __launch_bounds__(AT_NT, 1) attn_fwd_kernel(AttnArgs a) {
     extern __shared__ __align__(16) float at_smem[];
     const int b = blockIdx.y, q0 = blockIdx.x * QT, nq = min(QT, a.N - q0), Lp = (a.M + 3) & ~3;
-    float *strip = at_smem, *qs = strip + (size_t)QT * Lp + 16, *tile = qs + AT_DC * (QT + 8);
+    float *strip = at_smem, *qs = strip + (size_t)QT * Lp + 16, *tile = qs + AT_DC * at_qsp(QT);
     if (threadIdx.x < 16) strip[(size_t)QT * Lp + threadIdx.x] = 0.f;      // B fragments of the last row read up to 7 floats past its end
     strip_gemm<QT>(strip, Lp, a.M, a.theta + (size_t)b * a.D * a.N, a.N, q0, nq, a.phi + (size_t)b * a.D * a.M, a.M, a.D, qs, tile);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -258,7 +261,7 @@ template <int QT>
 __global__ void __launch_bounds__(AT_NT, 1) attn_bwd_q_kernel(AttnArgs a) {
     extern __shared__ __align__(16) float at_smem[];
     const int b = blockIdx.y, q0 = blockIdx.x * QT, nq = min(QT, a.N - q0), Lp = (a.M + 3) & ~3;
-    float *strip = at_smem, *qs = strip + (size_t)QT * Lp + 16, *tile = qs + AT_DC * (QT + 8);
+    float *strip = at_smem, *qs = strip + (size_t)QT * Lp + 16, *tile = qs + AT_DC * at_qsp(QT);
     if (threadIdx.x < 16) strip[(size_t)QT * Lp + threadIdx.x] = 0.f;      // B fragments of the last row read up to 7 floats past its end
     strip_gemm<QT>(strip, Lp, a.M, a.d_o + (size_t)b * a.Cv * a.N, a.N, q0, nq, a.g + (size_t)b * a.Cv * a.M, a.M, a.Cv, qs, tile);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -285,7 +288,7 @@ template <int QT>
 __global__ void __launch_bounds__(AT_NT, 1) attn_bwd_k_kernel(AttnArgs a) {
     extern __shared__ __align__(16) float at_smem[];
     const int b = blockIdx.y, m0 = blockIdx.x * QT, nk = min(QT, a.M - m0), Lp = (a.N + 3) & ~3;
-    float *strip = at_smem, *tile = strip + (size_t)QT * Lp + 16 + AT_DC * (QT + 8);
+    float *strip = at_smem, *tile = strip + (size_t)QT * Lp + 16 + AT_DC * at_qsp(QT);
     if (threadIdx.x < 16) strip[(size_t)QT * Lp + threadIdx.x] = 0.f;
     for (int pass = 0; pass < 2; ++pass) {
         const float *src = (pass == 0 ? a.ds : a.attn) + (size_t)b * a.N * a.M + m0;
