@@ -127,10 +127,10 @@ _SIGS = {
     "gssd_dcn_columns": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "gssd_dcn_columns_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "gssd_pmf32_to_nchw": (_I, [_P, _I, _I, _I, _I, _P, _P]),
-    "gssd_bn_relu_nchw_fwd": (_I, [_P, _P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P, _F, _P, _P]),
+    "gssd_bn_relu_nchw_fwd": (_I, [_P, _P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P, _F, _P, _P, _P]),
     "gssd_bn_relu_nchw_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "gssd_maxpool_nchw_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
-    "gssd_bn_relu_nhwc_fwd": (_I, [_P, _P, _P, C.c_long, _I, _F, _I, _P, _P, _P, _P, _F, _P, _P]),
+    "gssd_bn_relu_nhwc_fwd": (_I, [_P, _P, _P, C.c_long, _I, _F, _I, _P, _P, _P, _P, _F, _P, _P, _P]),
     "gssd_bn_relu_nhwc_bwd": (_I, [_P, _P, _P, _P, _P, C.c_long, _I, _I, _P, _P, _P, _P, _P]),
     "gssd_maxpool_nhwc_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "gssd_attn_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),

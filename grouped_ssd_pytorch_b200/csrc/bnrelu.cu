@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(BNR_NT) bnr_stats_kernel(const float *__restri
 __global__ void __launch_bounds__(BNR_NT) bnr_apply_kernel(const float *__restrict__ x, int C, int HW, bool aligned, const double *__restrict__ sums,
                                                            double inv_count, double unbias, float eps, const float *__restrict__ gamma,
                                                            const float *__restrict__ beta, int relu, float *__restrict__ y,
-                                                           float *__restrict__ save, float *running_mean, float *running_var, float momentum) {
+                                                           float *__restrict__ save, float *running_mean, float *running_var, float momentum,
+                                                           const float *__restrict__ mean_shift) {
     const size_t plane = blockIdx.x, off = plane * HW;
     const int c = (int)(plane % C);
     const BnCoef k = bn_coef(sums, c, inv_count, eps, gamma, beta);
@@ -84,7 +85,8 @@ __global__ void __launch_bounds__(BNR_NT) bnr_apply_kernel(const float *__restri
             const double mean = sums[2 * c] * inv_count;
             double var = sums[2 * c + 1] * inv_count - mean * mean;
             var = var < 0.0 ? 0.0 : var;
-            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+            // mean_shift: the bias of the convolution in front, which the caller left out (it cancels in the normalisation)
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * ((float)mean + (mean_shift ? mean_shift[c] : 0.f));
             running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * unbias);
         }
     }
@@ -244,7 +246,8 @@ __global__ void __launch_bounds__(BNH_NT) bnh_stats_kernel(const float4 *__restr
 __global__ void __launch_bounds__(BNH_NT) bnh_apply_kernel(const float4 *__restrict__ x, int C, size_t n4, const double *__restrict__ sums,
                                                            double inv_count, double unbias, float eps, const float *__restrict__ gamma,
                                                            const float *__restrict__ beta, int relu, float4 *__restrict__ y,
-                                                           float *__restrict__ save, float *running_mean, float *running_var, float momentum) {
+                                                           float *__restrict__ save, float *running_mean, float *running_var, float momentum,
+                                                           const float *__restrict__ mean_shift) {
     const int q = C / 4, quad = threadIdx.x % q;
     BnCoef k[4];
 #pragma unroll
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(BNH_NT) bnh_apply_kernel(const float4 *__restr
                 const double mean = sums[2 * c] * inv_count;
                 double var = sums[2 * c + 1] * inv_count - mean * mean;
                 var = var < 0.0 ? 0.0 : var;
-                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * ((float)mean + (mean_shift ? mean_shift[c] : 0.f));
                 running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * unbias);
             }
         }
@@ -414,7 +417,7 @@ using namespace gssd;
 
 extern "C" int gssd_bn_relu_nchw_fwd(const float *x, const float *gamma, const float *beta, int N, int C, int HW, float eps, int relu,
                                      float *y, float *save_mean_rstd, float *running_mean, float *running_var, float momentum,
-                                     double *ws, void *stream) {
+                                     const float *mean_shift, double *ws, void *stream) {
     if (!x || !gamma || !beta || !y || !save_mean_rstd || !ws) return GSSD_ERR_ARG;
     if ((running_mean == nullptr) != (running_var == nullptr)) return GSSD_ERR_ARG;
     int rc = bnr_check(N, C, HW);
@@ -427,7 +430,7 @@ extern "C" int gssd_bn_relu_nchw_fwd(const float *x, const float *gamma, const f
     bnr_stats_kernel<<<planes, BNR_NT, 0, st>>>(x, C, HW, al, ws);
     GSSD_AFTER_LAUNCH();
     bnr_apply_kernel<<<planes, BNR_NT, 0, st>>>(x, C, HW, al, ws, 1.0 / count, unbias, eps, gamma, beta, relu, y, save_mean_rstd, running_mean,
-                                                running_var, momentum);
+                                                running_var, momentum, mean_shift);
     GSSD_AFTER_LAUNCH();
     return GSSD_OK;
 }
@@ -475,7 +478,8 @@ extern "C" int gssd_maxpool_nchw_bwd(const float *dy, const int64_t *indices, in
 }
 
 extern "C" int gssd_bn_relu_nhwc_fwd(const float *x, const float *gamma, const float *beta, long rows, int C, float eps, int relu, float *y,
-                                     float *save_mean_rstd, float *running_mean, float *running_var, float momentum, double *ws, void *stream) {
+                                     float *save_mean_rstd, float *running_mean, float *running_var, float momentum, const float *mean_shift, double *ws,
+                                     void *stream) {
     if (!x || !gamma || !beta || !y || !save_mean_rstd || !ws) return GSSD_ERR_ARG;
     if ((running_mean == nullptr) != (running_var == nullptr)) return GSSD_ERR_ARG;
     int rc = bnh_check(rows, C, x, y, x);
@@ -488,7 +492,7 @@ extern "C" int gssd_bn_relu_nhwc_fwd(const float *x, const float *gamma, const f
     bnh_stats_kernel<<<grid, BNH_NT, 0, st>>>(reinterpret_cast<const float4 *>(x), C / 4, n4, ws);
     GSSD_AFTER_LAUNCH();
     bnh_apply_kernel<<<grid, BNH_NT, 0, st>>>(reinterpret_cast<const float4 *>(x), C, n4, ws, 1.0 / count, unbias, eps, gamma, beta, relu,
-                                              reinterpret_cast<float4 *>(y), save_mean_rstd, running_mean, running_var, momentum);
+                                              reinterpret_cast<float4 *>(y), save_mean_rstd, running_mean, running_var, momentum, mean_shift);
     GSSD_AFTER_LAUNCH();
     return GSSD_OK;
 }

@@ -363,11 +363,13 @@ GSSD_API int gssd_bn_relu_bwd_pm(const void *dy_bf16, const void *y_bf16, const 
  * variance) followed by F.relu, as two streaming kernels forward and two backward.
  *   x, y, dy, dx: [N, C, HW] contiguous; gamma / beta [C]; save_mean_rstd [2C] (mean, 1/sqrt(var+eps) per channel, written by the
  *   forward, read by the backward); running_mean / running_var [C] or both NULL; ws: 2C doubles of scratch (zeroed by the call).
+ *   mean_shift [C] or NULL: added to the batch mean in the running-mean update only — the bias of the convolution in front when the
+ *   caller ran that convolution without it (a per-channel constant cancels in the normalisation: BN(x + b) == BN(x)).
  *   backward: the ReLU mask is recomputed from x (y > 0  <=>  x*a + b > 0 with the forward's own coefficients).
  * ---------------------------------------------------------------------------------------- */
 GSSD_API int gssd_bn_relu_nchw_fwd(const float *x, const float *gamma, const float *beta, int N, int C, int HW, float eps, int relu,
-                          float *y, float *save_mean_rstd, float *running_mean, float *running_var, float momentum, double *ws,
-                          void *stream);
+                          float *y, float *save_mean_rstd, float *running_mean, float *running_var, float momentum,
+                          const float *mean_shift, double *ws, void *stream);
 GSSD_API int gssd_bn_relu_nchw_bwd(const float *x, const float *dy, const float *gamma, const float *beta, const float *save_mean_rstd,
                           int N, int C, int HW, int relu, float *dx, float *d_gamma, float *d_beta, double *ws, void *stream);
 
@@ -380,7 +382,8 @@ GSSD_API int gssd_maxpool_nchw_bwd(const float *dy, const int64_t *indices, int 
 /* The same three operators on channels-last tensors (torch.channels_last: [rows = N*H*W, C] with the channels innermost), for a
  * backbone whose convolutions run on cuDNN's NHWC kernels.  C must be 4 times a power of two, at most 1024. */
 GSSD_API int gssd_bn_relu_nhwc_fwd(const float *x, const float *gamma, const float *beta, long rows, int C, float eps, int relu, float *y,
-                          float *save_mean_rstd, float *running_mean, float *running_var, float momentum, double *ws, void *stream);
+                          float *save_mean_rstd, float *running_mean, float *running_var, float momentum, const float *mean_shift,
+                          double *ws, void *stream);
 GSSD_API int gssd_bn_relu_nhwc_bwd(const float *x, const float *dy, const float *gamma, const float *beta, const float *save_mean_rstd,
                           long rows, int C, int relu, float *dx, float *d_gamma, float *d_beta, double *ws, void *stream);
 GSSD_API int gssd_maxpool_nhwc_bwd(const float *dy, const int64_t *indices, int N, int C, int H, int W, int OH, int OW, int kernel, int stride,
