@@ -29,7 +29,7 @@ def run(N, C=1024, O=512, H=38, W=38, dg=4):
     x = torch.randn(N, C, H, W, device=DEV)
     w = (torch.randn(O, C, 3, 3, device=DEV) / (9 * C) ** 0.5).requires_grad_(True)
     b = torch.zeros(O, device=DEV, requires_grad=True)
-    off = (1.5 * torch.randn(N, 2 * dg * 9, H, W, device=DEV)).requires_grad_(True)
+    off = (float(os.environ.get("DCN_OFF", "1.5")) * torch.randn(N, 2 * dg * 9, H, W, device=DEV)).requires_grad_(True)   # std of the offsets, pixels
     msk = torch.sigmoid(torch.randn(N, dg * 9, H, W, device=DEV)).requires_grad_(True)
     gout = torch.randn(N, O, H, W, device=DEV)
     xg = x.clone().requires_grad_(True)
