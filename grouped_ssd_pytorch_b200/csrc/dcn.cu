@@ -241,7 +241,8 @@ __global__ void __launch_bounds__(DCN_WARPS * 32) dcn_columns_bwd_kernel(const _
                 float *q = dx + cur.q;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (flags & (DCN_PIX0 << k)) {
+                    if ((flags & (DCN_PIX0 << k)) && cur.rec[k] != 0.f) {      // (samples on the pixel grid — the module's zero-initialised
+                                                                                // offsets — touch one neighbour, not four)
                         float *tq = q + (size_t)((k >> 1) * wp + (k & 1)) * c_in;
                         const float a = m * cur.rec[k];
                         red_add_v4(tq, a * d[0], a * d[1], a * d[2], a * d[3]);
