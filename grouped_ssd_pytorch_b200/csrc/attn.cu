@@ -290,19 +290,20 @@ __global__ void __launch_bounds__(AT_NT, 1) attn_bwd_k_kernel(AttnArgs a) {
     const int b = blockIdx.y, m0 = blockIdx.x * QT, nk = min(QT, a.M - m0), Lp = (a.N + 3) & ~3;
     float *strip = at_smem, *tile = strip + (size_t)QT * Lp + 16 + AT_DC * at_qsp(QT);
     if (threadIdx.x < 16) strip[(size_t)QT * Lp + threadIdx.x] = 0.f;
-    for (int pass = 0; pass < 2; ++pass) {
-        const float *src = (pass == 0 ? a.ds : a.attn) + (size_t)b * a.N * a.M + m0;
-        __syncthreads();
-        for (int e = threadIdx.x; e < QT * Lp; e += AT_NT) {
-            const int q = e / QT, kl = e - q * QT;                    // consecutive threads: consecutive keys of one query row
-            strip[(size_t)kl * Lp + q] = (q < a.N && kl < nk) ? tf32r(src[(size_t)q * a.M + kl]) : 0.f;
-        }
-        __syncthreads();
-        if (pass == 0)
-            apply_any<QT>(strip, Lp, a.N, a.theta + (size_t)b * a.D * a.N, a.N, a.D, a.d_phi + (size_t)b * a.D * a.M, a.M, m0, nk, tile);
-        else
-            apply_any<QT>(strip, Lp, a.N, a.d_o + (size_t)b * a.Cv * a.N, a.N, a.Cv, a.d_g + (size_t)b * a.Cv * a.M, a.M, m0, nk, tile);
+    // blockIdx.z picks the product: 0 = d_phi from dS, 1 = d_g from the attention map.  Two CTAs per key strip instead of one that
+    // does both: at 4 images 244 CTAs were two rounds on 148 SMs, the second two thirds empty; 488 half-size ones pack better
+    const int pass = blockIdx.z;
+    const float *src = (pass == 0 ? a.ds : a.attn) + (size_t)b * a.N * a.M + m0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < QT * Lp; e += AT_NT) {
+        const int q = e / QT, kl = e - q * QT;                        // consecutive threads: consecutive keys of one query row
+        strip[(size_t)kl * Lp + q] = (q < a.N && kl < nk) ? tf32r(src[(size_t)q * a.M + kl]) : 0.f;
     }
+    __syncthreads();
+    if (pass == 0)
+        apply_any<QT>(strip, Lp, a.N, a.theta + (size_t)b * a.D * a.N, a.N, a.D, a.d_phi + (size_t)b * a.D * a.M, a.M, m0, nk, tile);
+    else
+        apply_any<QT>(strip, Lp, a.N, a.d_o + (size_t)b * a.Cv * a.N, a.N, a.Cv, a.d_g + (size_t)b * a.Cv * a.M, a.M, m0, nk, tile);
 }
 
 static int attn_check(const AttnArgs &a, int B) {
@@ -321,9 +322,9 @@ static int attn_pick_qt(int L, int D) {
 }
 
 template <typename K>
-static int attn_launch(K kern, const AttnArgs &a, int B, int tiles, size_t smem, cudaStream_t st) {
+static int attn_launch(K kern, const AttnArgs &a, int B, int tiles, size_t smem, cudaStream_t st, int nz = 1) {
     GSSD_RETURN_IF_CUDA(allow_max_smem(reinterpret_cast<const void *>(kern)));
-    kern<<<dim3(tiles, B), AT_NT, smem, st>>>(a);
+    kern<<<dim3(tiles, B, nz), AT_NT, smem, st>>>(a);
     GSSD_AFTER_LAUNCH();
     return GSSD_OK;
 }
@@ -369,8 +370,8 @@ extern "C" int gssd_attn_bwd(const float *theta, const float *phi, const float *
     }
     if (rc) return rc;
     switch (kt) {
-        case 24: return attn_launch(attn_bwd_k_kernel<24>, a, B, ceil_div(M, 24), smem_k, st);
-        case 16: return attn_launch(attn_bwd_k_kernel<16>, a, B, ceil_div(M, 16), smem_k, st);
-        default: return attn_launch(attn_bwd_k_kernel<8>, a, B, ceil_div(M, 8), smem_k, st);
+        case 24: return attn_launch(attn_bwd_k_kernel<24>, a, B, ceil_div(M, 24), smem_k, st, 2);
+        case 16: return attn_launch(attn_bwd_k_kernel<16>, a, B, ceil_div(M, 16), smem_k, st, 2);
+        default: return attn_launch(attn_bwd_k_kernel<8>, a, B, ceil_div(M, 8), smem_k, st, 2);
     }
 }
