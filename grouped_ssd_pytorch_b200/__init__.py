@@ -64,6 +64,7 @@ def install_as_layers(provide_data=True, reference_root=None, reference_modules=
         mod = importlib.util.module_from_spec(spec)
         sys.modules["layers." + sub] = mod
         spec.loader.exec_module(mod)
+        setattr(_layers, sub, mod)          # `from layers import self_attn` reads the package attribute, not sys.modules
     if provide_data and "data" not in sys.modules:
         try:
             found = importlib.util.find_spec("data") is not None

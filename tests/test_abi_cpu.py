@@ -268,3 +268,55 @@ def test_synthetic_inputs_are_reproducible():
     assert all(1 <= t.shape[0] <= 5 and t.shape[1] == 5 and (t[:, 2] >= t[:, 0]).all() for t in a)
     s = syn.detect_scores(syn.rng(1), 2, 1000, 2, -4.0)
     assert 0.005 < (s[..., 1] > 0.2).mean() < 0.08
+
+
+def test_run_layers_leaves_cpu_tensors_to_torch():
+    """layers/modules/bn_relu.py on a CPU box: nothing is taken, every module runs as itself (no CUDA call, no error)"""
+    import torch.nn as nn
+    from grouped_ssd_pytorch_b200.layers.modules import bn_relu as BR
+    torch.manual_seed(0)
+    mods = nn.ModuleList([nn.Conv2d(4, 8, 3, padding=1), nn.BatchNorm2d(8), nn.ReLU(inplace=True), nn.MaxPool2d(2, 2, ceil_mode=True),
+                          nn.Conv2d(8, 8, 1), nn.BatchNorm2d(8)]).train()
+    import copy
+    ref = copy.deepcopy(nn.Sequential(*mods))
+    x = torch.randn(2, 4, 7, 7)
+    assert not BR.takes(x, mods[1])
+    assert torch.equal(BR.run_layers(mods, x), ref(x))
+    assert torch.equal(mods[1].running_mean, ref[1].running_mean) and int(mods[1].num_batches_tracked) == 1
+    x8 = torch.randn(2, 8, 7, 7)
+    assert torch.equal(BR.run_layers(mods, x8, 3, 5), ref[4](ref[3](x8)))                 # a slice of the list
+    assert BR._pool_geometry(nn.MaxPool2d(2, 2)) == (2, 2, 0) and BR._pool_geometry(nn.MaxPool2d(3, 1, 1)) == (3, 1, 1)
+    assert BR._pool_geometry(nn.MaxPool2d((3, 2))) is None and BR._pool_geometry(nn.MaxPool2d(2, dilation=2)) is None
+    assert BR._pool_geometry(nn.MaxPool2d(2, return_indices=True)) is None
+    with pytest.raises(NotImplementedError):
+        BR.bn_relu(x, mods[1])
+
+
+def test_provide_dcn_v2_registers_this_packages_operator():
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import grouped_ssd_pytorch_b200 as g\n"
+            "m = g.provide_dcn_v2()\n"
+            "import dcn_v2\n"
+            "from grouped_ssd_pytorch_b200.layers import dcn_v2_custom as D\n"
+            "assert dcn_v2 is m and dcn_v2._DCNv2 is D._DCNv2 and dcn_v2.DCN is D.DCN\n"
+            "print('OK')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference tree (build container)")
+def test_install_as_layers_can_keep_the_references_gssdpp_modules():
+    import subprocess
+    code = ("import sys, types; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "d = types.ModuleType('dcn_v2'); d._DCNv2 = type('_DCNv2', (), {'apply': None}); sys.modules['dcn_v2'] = d\n"
+            "import grouped_ssd_pytorch_b200 as g\n"
+            "g.install_as_layers(reference_modules=('dcn_v2_custom', 'self_attn'))\n"
+            "from layers.dcn_v2_custom import DCN\n"
+            "from layers import self_attn\n"
+            "from layers.modules import MultiBoxLoss\n"
+            "assert sys.modules['layers.dcn_v2_custom'].__file__.startswith(%r) and self_attn.__file__.startswith(%r)\n"
+            "assert MultiBoxLoss.__module__.startswith('grouped_ssd_pytorch_b200')\n"
+            "print('OK')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), REF, REF, REF)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"))
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
