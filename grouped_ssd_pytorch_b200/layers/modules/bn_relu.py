@@ -158,15 +158,25 @@ def to_channels_last(modules):
                 m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
 
 
-def run_layers(modules, x, start=0, stop=None, skip_bias=True):
+def run_layers(modules, x, start=0, stop=None, skip_bias=True, tc=None):
     """x through modules[start:stop]; every training-mode (BatchNorm2d, ReLU) pair runs as one fused node, a BatchNorm2d without a
     ReLU behind it as the same kernels without the clamp, a convolution in front of such a BatchNorm2d without its bias add (see
-    bn_relu), an nn.MaxPool2d with the gather backward, everything else as the module itself."""
+    bn_relu), an nn.MaxPool2d with the gather backward, everything else as the module itself.
+    tc: a dict (the caller's cache of packed layers) turns on the tcgen05 path for the grouped backbone convolutions: every run of
+    (Conv2d, training-mode BatchNorm2d, ReLU) triples with 64 / 128 channels per group (conv3_2 .. conv5_3 of the reference's vgg
+    list) runs in bf16 on the PM layout, forward and backward (source_block.PMConvLayer)."""
     stop = len(modules) if stop is None else stop
     k = start
     while k < stop:
         m = modules[k]
         nxt = modules[k + 1] if k + 1 < stop else None
+        if tc is not None and isinstance(m, nn.Conv2d) and isinstance(nxt, nn.BatchNorm2d):
+            from .source_block import pm_layers_at, run_pm_layers
+            pairs = pm_layers_at(modules, k, stop, x)
+            if pairs:
+                x = run_pm_layers(pairs, x, tc)
+                k += 3 * len(pairs)
+                continue
         if (skip_bias and isinstance(m, nn.Conv2d) and m.bias is not None and m.padding_mode == "zeros" and isinstance(nxt, nn.BatchNorm2d)
                 and isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32):
             # convolution -> training-mode BatchNorm: torch's separate bias-add pass behind the cuDNN convolution and the reduction over

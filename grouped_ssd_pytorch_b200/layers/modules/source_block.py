@@ -554,6 +554,187 @@ class _SourceChainFn(torch.autograd.Function):
         return tuple(out)
 
 
+# ---- the grouped backbone convolutions under autograd (second half) -------------------------------------------------
+# conv3_2 .. conv5_3 of the reference's vgg list (ssd_multiphase_custom_group.py:434-460) are [Conv2d(groups=4), BatchNorm2d, ReLU]
+# triples with 64 or 128 channels per group: each runs as one autograd node on the kernels of the source block — forward
+# gssd_conv_igemm + gssd_bn_act_pm_to, backward gssd_bn_relu_bwd_pm + gssd_conv_wgrad + gssd_conv_igemm on the rotated filter — with
+# bf16 PM tensors (and bf16 PM gradients) flowing between consecutive triples.
+class _NchwToPMFn(torch.autograd.Function):
+    """NCHW fp32 -> the bf16 [rows, c] tensor of a PM; the gradient comes back as such a tensor and leaves as NCHW fp32"""
+
+    @staticmethod
+    def forward(ctx, x):
+        pm = PM.from_nchw(x)
+        ctx.geom = (pm.n, pm.c, pm.h, pm.w)
+        return pm.data
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d):
+        return PM(d.contiguous(), *ctx.geom).to_nchw()
+
+
+class _PMToNchwFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data, n, c, h, w):
+        return PM(data, n, c, h, w).to_nchw()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        return PM.from_nchw(dy).data, None, None, None, None
+
+
+class _Filter(object):
+    """what _Conv reads of an nn.Conv2d, for filters that are not a module's parameter (the rotated filter of a data gradient)"""
+
+    def __init__(self, weight, k):
+        self.weight, self.bias = weight, None
+        self.kernel_size, self.stride, self.dilation, self.padding = (k, k), (1, 1), (1, 1), (k // 2, k // 2)
+
+
+def _wgrad_any(dy, x, c_out, groups, taps):
+    """_wgrad for every group width the forward kernel takes.  gssd_conv_wgrad's tiles are 128 channels wide; with 64 channels per
+    group, neighbouring groups are handed to it as ONE group of 128 and the cross-group blocks it computes on the way (the gradient
+    of filter entries a grouped convolution does not have) are dropped."""
+    cg, ng = x.c // groups, c_out // groups
+    if cg % 128 == 0 and (groups == 1 or ng % 128 == 0):
+        return _wgrad(dy, x, c_out, groups, taps)
+    m = 128 // cg if (cg > 0 and 128 % cg == 0) else 0
+    if m < 2 or groups % m or (m * ng) % 128:
+        raise NotImplementedError("weight gradient for %d -> %d channels in %d groups" % (x.c, c_out, groups))
+    full = _wgrad(dy, x, c_out, groups // m, taps)                        # [c_out, m*cg, k, k]
+    k = full.shape[-1]
+    t = full.view(groups // m, m, ng, m, cg, k, k)
+    return torch.stack([t[:, j, :, j] for j in range(m)], 1).reshape(c_out, cg, k, k)
+
+
+class PMConvLayer(object):
+    """one (Conv2d, BatchNorm2d in training mode, ReLU) triple of the backbone on PM tensors"""
+    calls = 0                                                             # forward calls so far (tests / bench: the path was taken)
+    debug_outputs = None                                                  # tests: a list that receives every forward's output (NCHW fp32)
+
+    def __init__(self, conv, bn):
+        self.conv, self.bn = conv, bn
+        self._fwd = self._dg = None
+
+    @staticmethod
+    def takes(conv, bn, relu, x=None, width=None):
+        """x: the NCHW input of the triple (checked when given); width: the feature-map width when only that is known"""
+        import torch.nn as nn
+        if not (_conv_eligible(conv) and isinstance(bn, nn.BatchNorm2d) and isinstance(relu, nn.ReLU)):
+            return False
+        if not bn.training or bn.num_features != conv.out_channels or conv.padding_mode != "zeros":
+            return False
+        cg, ng, g = conv.in_channels // conv.groups, conv.out_channels // conv.groups, conv.groups
+        wgrad_ok = (cg % 128 == 0 and (g == 1 or ng % 128 == 0)) or (cg == 64 and g % 2 == 0 and (2 * ng) % 128 == 0)
+        if not wgrad_ok or conv.out_channels % 256 or conv.out_channels > 1024:        # gssd_bn_relu_bwd_pm: whole 256-channel rows
+            return False
+        # widest feature map whose 3x3 slab ring fits twice beside the weight stages of gssd_conv_igemm (forward and data gradient):
+        # 128-column weight tiles leave room for slabs of up to 64 pixels per row, 64-column tiles for 150
+        w_max = 62 if (ng % 128 == 0 or cg % 128 == 0) else 150
+        if width is not None and width > w_max:
+            return False
+        return x is None or (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+                             and x.shape[1] == conv.in_channels and x.shape[3] <= w_max)
+
+    def fwd(self, dev):
+        key = (_versions(self.conv), str(dev))
+        if self._fwd is None or self._fwd[0] != key:
+            with torch.no_grad(), torch.cuda.device(dev):
+                self._fwd = (key, _Conv(self.conv, self.conv.groups, dev=dev))
+        return self._fwd[1]
+
+    def dgrad(self, dev):
+        key = (_versions(self.conv), str(dev))
+        if self._dg is None or self._dg[0] != key:
+            with torch.no_grad(), torch.cuda.device(dev):
+                g = self.conv.groups
+                wd = dgrad_weight(_lib.f32(self.conv.weight, dev), g)
+                self._dg = (key, _Conv(_Filter(wd, wd.shape[2]), g, dev=dev))
+        return self._dg[1]
+
+    def __call__(self, xdata, n, h, w):
+        """xdata: bf16 [n*(h+2)*(w+2), c_in] -> bf16 [rows, c_out] (the ReLU output), recorded by autograd"""
+        conv, bn = self.conv, self.bn
+        gamma, beta = (bn.weight, bn.bias) if bn.affine else (None, None)
+        return _PMConvBnReluFn.apply(xdata, self, n, h, w, conv.weight, conv.bias, gamma, beta)
+
+
+class _PMConvBnReluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xdata, layer, n, h, w, weight, bias, gamma, beta):
+        dev = xdata.device
+        conv, bn = layer.conv, layer.bn
+        with torch.cuda.device(dev):
+            x0 = PM(xdata, n, conv.in_channels, h, w)
+            cv = layer.fwd(dev)
+            stats = torch.zeros((2 * cv.c_out,), dtype=torch.float32, device=dev)
+            yraw = conv_igemm(x0, cv, relu=False, shift=cv.bias, chan_sum=stats)
+            y = PM.empty(n, cv.c_out, h, w, dev)
+            SourceBlock._bn_train(yraw, bn, stats, False, out=y)
+        PMConvLayer.calls += 1
+        if PMConvLayer.debug_outputs is not None:
+            PMConvLayer.debug_outputs.append(y.to_nchw())
+        ctx.layer, ctx.geom = layer, (n, h, w)
+        ctx.save_for_backward(xdata, yraw.data, y.data, stats)
+        return y.data
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        xdata, yraw_d, y_d, stats = ctx.saved_tensors
+        layer = ctx.layer
+        n, h, w = ctx.geom
+        conv, bn = layer.conv, layer.bn
+        dev = xdata.device
+        c_in, c_out = conv.in_channels, conv.out_channels
+        with torch.cuda.device(dev):
+            x0, yraw, y = PM(xdata, n, c_in, h, w), PM(yraw_d, n, c_out, h, w), PM(y_d, n, c_out, h, w)
+            d = PM(dy.to(torch.bfloat16).contiguous(), n, c_out, h, w)
+            gam = _lib.f32(bn.weight, dev) if bn.affine else None
+            d1, s = _bn_relu_bwd(d, y, yraw, None, stats, gam, bn.eps, None, 0.0, None, 0.0)
+            dw = _wgrad_any(d1, x0, c_out, conv.groups, conv.kernel_size[0] * conv.kernel_size[1])
+            dx = conv_igemm(d1, layer.dgrad(dev), relu=False).data if ctx.needs_input_grad[0] else None
+        # the bias of a convolution in front of a training-mode BatchNorm has no gradient (the batch mean removes any per-channel
+        # constant); s[2c:] = sum of dx holds only the rounding noise of that zero
+        d_bias = torch.zeros_like(conv.bias) if conv.bias is not None else None
+        d_gamma = s[c_out:2 * c_out].to(bn.weight.dtype) if bn.affine else None
+        d_beta = s[:c_out].to(bn.bias.dtype) if bn.affine else None
+        return dx, None, None, None, None, dw.to(conv.weight.dtype), d_bias, d_gamma, d_beta
+
+
+def pm_layers_at(modules, k, stop, x):
+    """the run of consecutive (Conv2d, BatchNorm2d, ReLU) triples PMConvLayer takes, starting at modules[k]: -> list of (conv, bn)"""
+    run = []
+    c = None
+    if not (isinstance(x, torch.Tensor) and x.dim() == 4):
+        return run
+    while k + 3 <= stop:
+        conv, bn, relu = modules[k], modules[k + 1], modules[k + 2]
+        if not PMConvLayer.takes(conv, bn, relu, x if not run else None, x.shape[3]) or (run and conv.in_channels != c):
+            break
+        run.append((conv, bn))
+        c = conv.out_channels
+        k += 3
+    return run
+
+
+def run_pm_layers(pairs, x, cache):
+    """x (NCHW fp32) through a run of triples (see pm_layers_at); `cache`: dict that keeps the PMConvLayer of every conv"""
+    n, _, h, w = x.shape
+    data = _NchwToPMFn.apply(x)
+    c = x.shape[1]
+    for conv, bn in pairs:
+        layer = cache.get(id(conv))
+        if layer is None or layer.conv is not conv or layer.bn is not bn:
+            layer = PMConvLayer(conv, bn)
+            cache[id(conv)] = layer
+        data = layer(data, n, h, w)
+        c = conv.out_channels
+    return _PMToNchwFn.apply(data, n, c, h, w)
+
+
 # ---- the model's forward with the source blocks swapped in ---------------------------------------------------
 def build_source_blocks(net):
     """SourceBlocks for the six sources of a reference `SSD` (ssd_type gssd: no self-attention, no DCN), built from
@@ -588,9 +769,11 @@ def gssd_forward(net, x, detect_args=(0, 200, 0.01, 0.45), backbone=False):
 
         net.forward = types.MethodType(gssd_forward, net)        # drop-in
 
-    backbone=True (opt-in, eval mode) also runs every grouped backbone conv the kernel takes — conv3_2 .. conv5_3, with
-    BatchNorm folded, ReLU fused and the pools on the PM layout — in bf16: 1.5x the model's fp32 torch forward at batch 32,
-    at 1.0e-2 / 6.6e-3 relative error on loc / conf instead of 6.0e-3 / 3.7e-3 (tests/test_gpu_model.py).
+    backbone=True (opt-in) also runs every grouped backbone conv the kernel takes — conv3_2 .. conv5_3 — in bf16.  Eval mode without
+    autograd: BatchNorm folded, ReLU fused and the pools on the PM layout (BackboneRun): 1.5x the model's fp32 torch forward at
+    batch 32, at 1.0e-2 / 6.6e-3 relative error on loc / conf instead of 6.0e-3 / 3.7e-3 (tests/test_gpu_model.py).  Training mode:
+    every (Conv2d, BatchNorm2d, ReLU) triple of that stretch is one autograd node on the same kernels as the source blocks
+    (PMConvLayer: batch statistics, data gradient on the forward kernel, weight gradient on gssd_conv_wgrad), the pools stay torch's.
     """
     import contextlib
     import os
@@ -663,13 +846,19 @@ def gssd_forward(net, x, detect_args=(0, 200, 0.01, 0.45), backbone=False):
                     to_channels_last(net.vgg)
                     net._gssd_channels_last = True
                 x = x.contiguous(memory_format=torch.channels_last)
-            x = run_layers(net.vgg, x, 0, i43) if fuse_bn else _plain(net.vgg, x, 0, i43)      # GSSD:254-259, up to the input of conv4_3
+            # backbone=True in training mode: conv3_2 .. conv5_3 on the tcgen05 kernels too, forward and backward (PMConvLayer)
+            tc = None
+            if backbone and net.training and fuse_bn:
+                tc = getattr(net, "_gssd_pm_layers", None)
+                if tc is None:
+                    tc = net._gssd_pm_layers = {}
+            x = run_layers(net.vgg, x, 0, i43, tc=tc) if fuse_bn else _plain(net.vgg, x, 0, i43)      # GSSD:254-259, up to the input of conv4_3
             x1 = run_block(blocks[0], x)                         # conv4_3 .. heads of source 1 (GSSD:258-297, 375-377)
             x = x1 if use_ag else x1.to_nchw()                   # post-ReLU conv4_3 continues down the backbone
             if chl:
                 x = x.contiguous(memory_format=torch.channels_last)
             k0 = i43 + (3 if bn else 2)                          # GSSD:300-301 up to the input of conv7
-            x = run_layers(net.vgg, x, k0, i7) if fuse_bn else _plain(net.vgg, x, k0, i7)
+            x = run_layers(net.vgg, x, k0, i7, tc=tc) if fuse_bn else _plain(net.vgg, x, k0, i7)
             x2 = run_block(blocks[1], x)                         # conv7 .. heads of source 2 (GSSD:300-325)
         x = x2 if use_ag else x2.to_nchw()
         si = 2
