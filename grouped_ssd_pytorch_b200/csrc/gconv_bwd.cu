@@ -224,8 +224,10 @@ struct BnBwdArgs {
     int relu;
 };
 
-template <bool APPLY>
-__global__ void __launch_bounds__(256) bn_bwd_pm_kernel(BnBwdArgs a) {
+// SLOTS = c / 256 groups of 8 channels per lane: the accumulators are sized for it, so that the 256- and 512-channel layers of the
+// backbone keep several CTAs per SM (sized for 1024 channels the APPLY pass needs 254 registers: one CTA of 8 warps per SM)
+template <bool APPLY, int SLOTS>
+__global__ void __launch_bounds__(256, SLOTS == 1 ? 4 : (SLOTS == 2 ? 2 : 1)) bn_bwd_pm_kernel(BnBwdArgs a) {
     extern __shared__ float sm[];                                           // [4][c]: mean, rstd, A = mean(g), Bc = mean(g*x_hat); then partial sums
     const int c = a.c;
     float *s_mean = sm, *s_rstd = sm + c, *s_mg = sm + 2 * c, *s_mgx = sm + 3 * c;
@@ -243,12 +245,11 @@ __global__ void __launch_bounds__(256) bn_bwd_pm_kernel(BnBwdArgs a) {
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    const int per_lane = c / 32;                                            // channels per lane: c % 256 == 0 -> multiples of 8
     // per-lane channel-sum accumulators live in shared memory after the row loop (c can be 1024: 32 per lane)
     const bool ebn = APPLY && !stats && a.ebn_w != nullptr;
-    float acc0[32], acc1[32], acc2[32];
+    float acc0[8 * SLOTS], acc1[8 * SLOTS], acc2[8 * SLOTS];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; acc2[j] = 0.f; }
+    for (int j = 0; j < 8 * SLOTS; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; acc2[j] = 0.f; }
     for (int m = blockIdx.x * wpb + warp; m < a.rows; m += gridDim.x * wpb) {
         const int rem = m % (a.hp * a.wp), py = rem / a.wp, px = rem - py * a.wp;
         const bool interior = py >= 1 && py <= a.h && px >= 1 && px <= a.w;
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(256) bn_bwd_pm_kernel(BnBwdArgs a) {
         }
         const float rs_out = a.row_ss_out ? 1.f / (sqrtf(a.row_ss_out[m]) + a.l2_eps_out) : 1.f;
 #pragma unroll
-        for (int slot = 0; slot < 4; ++slot) {                              // c <= 1024: at most 4 groups of 8 channels per lane
+        for (int slot = 0; slot < SLOTS; ++slot) {                          // c <= 1024: at most 4 groups of 8 channels per lane
             const int i = lane + 32 * slot;
             if (i >= c / 8) break;
             const uint4 q = dyr[i], r = yr[i];
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(256) bn_bwd_pm_kernel(BnBwdArgs a) {
     __syncthreads();
     {
 #pragma unroll
-        for (int slot = 0; slot < 4; ++slot) {
+        for (int slot = 0; slot < SLOTS; ++slot) {
             const int i = lane + 32 * slot;
             if (i >= c / 8) break;
 #pragma unroll
@@ -348,6 +349,21 @@ __global__ void __launch_bounds__(256) bn_bwd_pm_kernel(BnBwdArgs a) {
             if (ebn) { atomicAdd(a.sums + i, s_c[i]); atomicAdd(a.sums + c + i, s_b[i]); }
         }
     }
+}
+
+// one CTA of 8 warps per 8 pixel rows, at most as many CTAs as are resident at once (the row loop strides over the rest)
+template <int SLOTS>
+static int launch_bn_bwd_pm(const BnBwdArgs &a, long rows, size_t smem, bool reduce_first, cudaStream_t st) {
+    const long want = (rows + 7) / 8;
+    if (reduce_first) {
+        const int cap = resident_ctas(reinterpret_cast<const void *>(bn_bwd_pm_kernel<false, SLOTS>), 256, smem);
+        bn_bwd_pm_kernel<false, SLOTS><<<(int)(want < cap ? want : cap), 256, smem, st>>>(a);
+        GSSD_AFTER_LAUNCH();
+    }
+    const int cap = resident_ctas(reinterpret_cast<const void *>(bn_bwd_pm_kernel<true, SLOTS>), 256, smem);
+    bn_bwd_pm_kernel<true, SLOTS><<<(int)(want < cap ? want : cap), 256, smem, st>>>(a);
+    GSSD_AFTER_LAUNCH();
+    return GSSD_OK;
 }
 
 }  // namespace gssd
@@ -445,16 +461,11 @@ extern "C" int gssd_bn_relu_bwd_pm(const void *dy_bf16, const void *y_bf16, cons
     a.sums = sums; a.relu = relu;
     cudaStream_t st = (cudaStream_t)stream;
     GSSD_RETURN_IF_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 3 * (size_t)c, st));
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int blocks = (int)((rows + 7) / 8 < (long)sms * 2 ? (rows + 7) / 8 : (long)sms * 2);
     const size_t smem = 4 * (size_t)c * sizeof(float);
-    if (chan_sum != nullptr) {                                              // batch statistics: the sums come first
-        bn_bwd_pm_kernel<false><<<blocks, 256, smem, st>>>(a);
-        GSSD_AFTER_LAUNCH();
+    const bool reduce_first = chan_sum != nullptr;                           // batch statistics: the sums come first
+    switch (c / 256) {
+        case 1: return launch_bn_bwd_pm<1>(a, rows, smem, reduce_first, st);
+        case 2: return launch_bn_bwd_pm<2>(a, rows, smem, reduce_first, st);
+        default: return launch_bn_bwd_pm<4>(a, rows, smem, reduce_first, st);
     }
-    bn_bwd_pm_kernel<true><<<blocks, 256, smem, st>>>(a);
-    GSSD_AFTER_LAUNCH();
-    return GSSD_OK;
 }

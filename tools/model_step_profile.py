@@ -1,4 +1,4 @@
-"""torch.profiler kernel table of the GSSD training step of bench.py's `model_step` (batch 32): python tools/model_step_profile.py [torch|gssd]"""
+"""torch.profiler kernel table of the GSSD training step of bench.py's `model_step` (batch 32): python tools/model_step_profile.py [torch|gssd|backbone]"""
 import os, sys, types
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -17,7 +17,10 @@ x = G.seeded_input(72, B).to(dev)
 targets = [torch.from_numpy(t).to(dev) for t in syn.targets(syn.rng(5), B, 1, 5)]
 crit = MultiBoxLoss(2, 0.5, True, 0, True, 3, 0.5, False, True); crit.process_group = False
 fast = types.MethodType(gssd_forward, net)
-fwd = fast if mode == "gssd" else (lambda xx: G.forward_torch(net, xx) + (net.priors,))
+if mode == "backbone":                                       # conv3_2 .. conv5_3 on the tcgen05 kernels too
+    fwd = lambda xx: gssd_forward(net, xx, backbone=True)
+else:
+    fwd = fast if mode == "gssd" else (lambda xx: G.forward_torch(net, xx) + (net.priors,))
 def step():
     net.zero_grad(set_to_none=True)
     ll, lc = crit(fwd(x), targets)
@@ -28,4 +31,4 @@ torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     step(); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=90))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=90))
