@@ -227,10 +227,16 @@ struct BnBwdArgs {
 // SLOTS = c / 256 groups of 8 channels per lane: the accumulators are sized for it, so that the 256- and 512-channel layers of the
 // backbone keep several CTAs per SM (sized for 1024 channels the APPLY pass needs 254 registers: one CTA of 8 warps per SM)
 template <bool APPLY, int SLOTS>
-__global__ void __launch_bounds__(256, SLOTS == 1 ? 4 : (SLOTS == 2 ? 2 : 1)) bn_bwd_pm_kernel(BnBwdArgs a) {
-    extern __shared__ float sm[];                                           // [4][c]: mean, rstd, A = mean(g), Bc = mean(g*x_hat); then partial sums
+__global__ void __launch_bounds__(256, SLOTS == 1 ? 3 : (SLOTS == 2 ? 2 : 1)) bn_bwd_pm_kernel(BnBwdArgs a) {
+    // one float4 of coefficients per channel, read with ONE shared-memory load per element (separate mean / rstd / mean(g) /
+    // mean(g*x_hat) arrays plus gamma from global memory made the row loop issue-bound: 400 warp instructions per 256-channel row,
+    // 198 us for 32 x 75 x 75 x 256, ncu):   reduce pass (mean, rstd, -, -)      x_hat = (raw - mean) * rstd
+    //                                         apply pass  (mean, p, mg, k)        dx = k * (g - mg - (raw - mean) * p),
+    //                                         p = rstd * mean(g*x_hat), mg = mean(g), k = gamma * rstd   (no statistics: (0, 0, 0, gamma))
+    // afterwards the same memory holds the partial channel sums
+    extern __shared__ __align__(16) float sm[];
     const int c = a.c;
-    float *s_mean = sm, *s_rstd = sm + c, *s_mg = sm + 2 * c, *s_mgx = sm + 3 * c;
+    float4 *s_coef = reinterpret_cast<float4 *>(sm);
     const bool stats = a.chan_sum != nullptr;
     for (int i = threadIdx.x; i < c; i += blockDim.x) {
         float mean = 0.f, rstd = 1.f;
@@ -239,9 +245,13 @@ __global__ void __launch_bounds__(256, SLOTS == 1 ? 4 : (SLOTS == 2 ? 2 : 1)) bn
             const float var = fmaxf(a.chan_sum[c + i] * a.inv_count - mean * mean, 0.f);
             rstd = rsqrtf(var + a.bn_eps);
         }
-        s_mean[i] = mean; s_rstd[i] = rstd;
-        s_mg[i] = (APPLY && stats) ? a.sums[i] * a.inv_count : 0.f;
-        s_mgx[i] = (APPLY && stats) ? a.sums[c + i] * a.inv_count : 0.f;
+        if (!APPLY) {
+            s_coef[i] = make_float4(mean, rstd, 0.f, 0.f);
+        } else {
+            const float gam = a.gamma ? a.gamma[i] : 1.f;
+            s_coef[i] = stats ? make_float4(mean, rstd * (a.sums[c + i] * a.inv_count), a.sums[i] * a.inv_count, gam * rstd)
+                              : make_float4(0.f, 0.f, 0.f, gam);
+        }
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -301,14 +311,14 @@ __global__ void __launch_bounds__(256, SLOTS == 1 ? 4 : (SLOTS == 2 ? 2 : 1)) bn
                     const float d = e ? dv.y : dv.x, yy = e ? yv.y : yv.x, raw = e ? rv.y : rv.x, ad1 = e ? av.y : av.x;
                     float g = d - yy * l2_coef + ad1;
                     if (a.relu && !(yy > 0.f)) g = 0.f;
-                    const float xh = stats ? (raw - s_mean[ch]) * s_rstd[ch] : 0.f;
+                    const float4 cf = s_coef[ch];
                     if (!APPLY) {
+                        const float xh = stats ? (raw - cf.x) * cf.y : 0.f;
                         acc0[slot * 8 + 2 * j + e] += g;
                         acc1[slot * 8 + 2 * j + e] += g * xh;
                         res[e] = 0.f;
                     } else {
-                        const float gam = a.gamma ? a.gamma[ch] : 1.f;
-                        const float dx = stats ? gam * s_rstd[ch] * (g - s_mg[ch] - xh * s_mgx[ch]) : g * gam;
+                        const float dx = cf.w * (g - cf.z - (raw - cf.x) * cf.y);
                         acc0[slot * 8 + 2 * j + e] += dx;
                         if (ebn) {
                             const float bw = a.ebn_w[ch];
@@ -325,7 +335,7 @@ __global__ void __launch_bounds__(256, SLOTS == 1 ? 4 : (SLOTS == 2 ? 2 : 1)) bn
     }
     // channel sums: registers -> shared -> global atomics
     __syncthreads();
-    float *s_a = sm, *s_b = sm + c, *s_c = sm + 2 * c;                      // reuse (mean / rstd / means are dead)
+    float *s_a = sm, *s_b = sm + c, *s_c = sm + 2 * c;                      // reuse (the coefficients are dead)
     for (int i = threadIdx.x; i < 3 * c; i += blockDim.x) sm[i] = 0.f;
     __syncthreads();
     {
