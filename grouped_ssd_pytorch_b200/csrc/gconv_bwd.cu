@@ -245,12 +245,15 @@ __global__ void __launch_bounds__(256, SLOTS == 1 ? 3 : (SLOTS == 2 ? 2 : 1)) bn
             const float var = fmaxf(a.chan_sum[c + i] * a.inv_count - mean * mean, 0.f);
             rstd = rsqrtf(var + a.bn_eps);
         }
+        // channel i = (slot * 32 + lane) * 8 + k is kept at [(slot * 8 + k) * 32 + lane]: the 32 lanes of a warp, which read the same
+        // (slot, k) together, hit 32 consecutive float4 (in channel order they are 128 bytes apart: every lane on the same four banks)
+        const int at = ((i >> 8) * 8 + (i & 7)) * 32 + ((i >> 3) & 31);
         if (!APPLY) {
-            s_coef[i] = make_float4(mean, rstd, 0.f, 0.f);
+            s_coef[at] = make_float4(mean, rstd, 0.f, 0.f);
         } else {
             const float gam = a.gamma ? a.gamma[i] : 1.f;
-            s_coef[i] = stats ? make_float4(mean, rstd * (a.sums[c + i] * a.inv_count), a.sums[i] * a.inv_count, gam * rstd)
-                              : make_float4(0.f, 0.f, 0.f, gam);
+            s_coef[at] = stats ? make_float4(mean, rstd * (a.sums[c + i] * a.inv_count), a.sums[i] * a.inv_count, gam * rstd)
+                               : make_float4(0.f, 0.f, 0.f, gam);
         }
     }
     __syncthreads();
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(256, SLOTS == 1 ? 3 : (SLOTS == 2 ? 2 : 1)) bn
                     const float d = e ? dv.y : dv.x, yy = e ? yv.y : yv.x, raw = e ? rv.y : rv.x, ad1 = e ? av.y : av.x;
                     float g = d - yy * l2_coef + ad1;
                     if (a.relu && !(yy > 0.f)) g = 0.f;
-                    const float4 cf = s_coef[ch];
+                    const float4 cf = s_coef[(slot * 8 + 2 * j + e) * 32 + lane];
                     if (!APPLY) {
                         const float xh = stats ? (raw - cf.x) * cf.y : 0.f;
                         acc0[slot * 8 + 2 * j + e] += g;
