@@ -253,3 +253,37 @@ def _bn64(x, prm, name, eps, training):
 def _l2norm64(x, weight, eps=1e-10):
     n = np.sqrt((x ** 2).sum(axis=1, keepdims=True)) + eps
     return np.asarray(weight, np.float64)[None, :, None, None] * (x / n)
+
+
+# ---- the grouped backbone triples conv3_2 .. conv5_3 (models/ssd_multiphase_custom_group.py:434-460: nn.Conv2d(groups=4),
+# nn.BatchNorm2d, nn.ReLU; run by GSSD:254-259 / 300-301 as `x = self.vgg[k](x)`) — forward and backward in training mode ---------
+def backbone_triples(x, prm, gout=None, groups=4, eps=1e-5, momentum=0.1):
+    """x[N,C,H,W]; prm: list of dicts (w, b, gamma, beta) of consecutive [conv 3x3 pad 1, BatchNorm2d (batch statistics), ReLU]
+    triples -> dict(y, running statistics after one step from (0, 1)); with gout (upstream gradient of y) also
+    x / conv_w / conv_b / bn_w / bn_b gradients, keyed as tests/golden/backbone_bwd.npz.  Pinned against autograd on the reference's
+    own modules in float64 by tests/test_oracle_golden.py."""
+    h = np.asarray(x, np.float64)
+    saved, out = [], {}
+    for t, p in enumerate(prm):
+        w, b = p["w"].astype(np.float64), p["b"].astype(np.float64)
+        z = _conv64(h, w, b, groups, 1)
+        mean, var = z.mean(axis=(0, 2, 3)), z.var(axis=(0, 2, 3))
+        n = z.shape[0] * z.shape[2] * z.shape[3]
+        out["%d.running_mean" % t] = momentum * mean
+        out["%d.running_var" % t] = (1 - momentum) * 1.0 + momentum * var * n / max(n - 1, 1)
+        a = (z - mean[None, :, None, None]) / np.sqrt(var[None, :, None, None] + eps) * p["gamma"].astype(np.float64)[None, :, None, None] \
+            + p["beta"].astype(np.float64)[None, :, None, None]
+        saved.append((h, w, z, mean, var, a))
+        h = np.maximum(a, 0)
+    out["y"] = h
+    if gout is None:
+        return out
+    d = np.asarray(gout, np.float64)
+    for t in range(len(prm) - 1, -1, -1):
+        hin, w, z, mean, var, a = saved[t]
+        d = d * (a > 0)
+        dz, dgamma, dbeta = batch_norm_backward(z, prm[t]["gamma"], mean, var, eps, True, d)
+        d, dw, db = conv2d_backward(hin, w, dz, groups, 1)
+        out.update({"%d.conv_w" % t: dw, "%d.conv_b" % t: db, "%d.bn_w" % t: dgamma, "%d.bn_b" % t: dbeta})
+    out["x"] = d
+    return out

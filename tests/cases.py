@@ -193,3 +193,34 @@ def sa_case(tag):
         prm[name + ".weight_orig"], prm[name + ".bias"] = w, 0.1 * f(co)
         prm[name + ".weight_u"], prm[name + ".weight_v"] = u.astype(np.float32), v.astype(np.float32)
     return f(B, C, H, H), prm, (f(B, C, H, H), f(B, C, H, H))
+
+
+# ---- the grouped backbone triples conv3_2 .. conv5_3 under autograd (source_block.PMConvLayer) ---------------------------------------
+# tag -> (seed, first index into the reference's vgg list, number of [Conv2d, BatchNorm2d, ReLU] triples, N, H, W)
+BACKBONE_CASES = {
+    "conv3_2-3": (701, 17, 2, 2, 9, 11),        # 256 -> 256 -> 256, 64 channels per group
+    "conv4_1-2": (702, 24, 2, 2, 8, 7),         # 256 -> 512 -> 512
+    "conv5_1-3": (703, 34, 3, 3, 6, 5),         # 512 -> 512 three times
+}
+BACKBONE_CHANNELS = {17: 256, 20: 256, 24: 256, 27: 512, 34: 512, 37: 512, 40: 512}      # input channels of vgg[k]; outputs: 256 / 512
+
+
+def backbone_case(tag):
+    """-> (x[N,C,H,W] fp32 (bf16-representable, post-ReLU), list of per-triple dicts (w, b, gamma, beta; conv weights
+    bf16-representable), upstream gradient of the last ReLU output)"""
+    from oracle.source_block import bf16_round
+    seed, first, n_triples, N, H, W = BACKBONE_CASES[tag]
+    r = np.random.RandomState(seed)
+    c_in = BACKBONE_CHANNELS[first]
+    x = bf16_round(np.maximum(r.randn(N, c_in, H, W), 0).astype(np.float32))
+    prm = []
+    for t in range(n_triples):
+        k = first + 3 * t
+        c_in = BACKBONE_CHANNELS[k]
+        c_out = 256 if k < 24 else 512
+        fan = (c_in // 4) * 9
+        prm.append(dict(w=bf16_round((r.randn(c_out, c_in // 4, 3, 3) * np.sqrt(2.0 / fan)).astype(np.float32)),
+                        b=(r.randn(c_out) * 0.1).astype(np.float32),
+                        gamma=r.uniform(0.5, 1.5, c_out).astype(np.float32), beta=(r.randn(c_out) * 0.2).astype(np.float32)))
+    gout = r.randn(N, prm[-1]["w"].shape[0], H, W).astype(np.float32)
+    return x, prm, gout

@@ -128,6 +128,56 @@ def test_pm_layers_against_torch_autograd(tag):
     assert e <= 1e-2 * len(specs) + 5e-3
 
 
+@pytest.mark.parametrize("tag", sorted(__import__("cases").BACKBONE_CASES))
+def test_pm_layers_against_the_reference_golden(tag):
+    """against autograd through the reference's OWN vgg modules in float64 (tests/golden/backbone_bwd.npz, made by
+    tests/golden/make_golden_backbone_bwd.py from a model of its build_ssd): the output and the running statistics within the bf16
+    tolerance; the gradients in the relative L2 sense (on these 50 - 100 pixel maps a ReLU mask entry that flips under the bf16
+    rounding of the forward moves single entries by far more than the rounding, as in tests/test_gpu_block.py)."""
+    import cases
+    torch.backends.cudnn.allow_tf32 = False
+    g = cases.golden("backbone_bwd")
+    x, prm, gout = cases.backbone_case(tag)
+    mods = []
+    for p in prm:
+        conv = nn.Conv2d(p["w"].shape[1] * 4, p["w"].shape[0], 3, padding=1, groups=4)          # vgg(): ssd_multiphase_custom_group.py:448-455
+        bn = nn.BatchNorm2d(p["w"].shape[0])
+        with torch.no_grad():
+            conv.weight.copy_(torch.from_numpy(p["w"])); conv.bias.copy_(torch.from_numpy(p["b"]))
+            bn.weight.copy_(torch.from_numpy(p["gamma"])); bn.bias.copy_(torch.from_numpy(p["beta"]))
+        mods += [conv, bn, nn.ReLU(inplace=True)]
+    mods = nn.ModuleList(mods).to(DEV).train()
+    xt = torch.from_numpy(x).to(DEV).requires_grad_()
+    c0 = SB.PMConvLayer.calls
+    y = run_layers(mods, xt, tc={})
+    assert SB.PMConvLayer.calls == c0 + len(prm)
+    y.backward(torch.from_numpy(gout).to(DEV))
+    torch.cuda.synchronize()
+    got = {"y": y.detach(), "x": xt.grad}
+    for t in range(len(prm)):
+        conv, bn = mods[3 * t], mods[3 * t + 1]
+        got.update({"%d.conv_w" % t: conv.weight.grad, "%d.conv_b" % t: conv.bias.grad, "%d.bn_w" % t: bn.weight.grad, "%d.bn_b" % t: bn.bias.grad})
+        for k, buf in (("running_mean", bn.running_mean), ("running_var", bn.running_var)):
+            ref = torch.from_numpy(g["%s/%d.%s" % (tag, t, k)]).to(DEV)
+            assert rel(buf, ref) <= 1e-2, (tag, t, k, rel(buf, ref))
+    names = sorted(k[len(tag) + 1:-len("_sample")] for k in g.files if k.startswith(tag + "/") and k.endswith("_sample"))
+    assert set(names) == set(got)
+    peers = max(np.abs(g[tag + "/" + n + "_sample"]).max() for n in names if n != "y")
+    errs = {}
+    for name in names:
+        flat = got[name].detach().double().cpu().numpy().reshape(-1)
+        step = max(1, flat.size // 1024)
+        ref = g[tag + "/" + name + "_sample"].astype(np.float64)
+        if name != "y" and np.abs(ref).max() < 1e-5 * peers:          # conv bias in front of a training-mode BatchNorm: zero
+            assert np.abs(flat).max() <= 1e-2 * peers, name
+            continue
+        errs[name] = float(np.linalg.norm(flat[::step][:1024] - ref) / max(np.linalg.norm(ref), 1e-30))
+    note("%s vs the reference's float64 autograd, relative L2 of the sampled entries: %s" % (tag, {k: "%.1e" % v for k, v in sorted(errs.items())}))
+    assert errs["y"] <= 2e-2, errs
+    bad = {k: v for k, v in errs.items() if v > 1.5e-1}             # (a torch emulation of the bf16 storage alone gives up to 7e-2)
+    assert not bad, bad
+
+
 def test_gssd_training_step_with_the_backbone_on_tcgen05():
     """gssd_forward(backbone=True) in training mode against gssd_forward() on the same model and batch: the seven layers are taken;
     outputs, losses, running statistics and gradients agree within the rounding of seven more bf16 layers.  The BatchNorms of the
