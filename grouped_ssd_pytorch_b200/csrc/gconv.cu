@@ -517,13 +517,18 @@ __global__ void __launch_bounds__(256) bn_act_pm_kernel(__nv_bfloat16 *y, __nv_b
                                                         const float *__restrict__ chan_sum, const float *__restrict__ gamma,
                                                         const float *__restrict__ beta, float bn_eps, float inv_count, int relu,
                                                         float *__restrict__ row_ss_out) {
-    extern __shared__ float coef[];                                          // [2][c] : a = rstd*gamma, b = beta - mean*a
+    // per channel (a, b) = (rstd*gamma, beta - mean*a) as one float2.  With whole groups of 256 channels, channel
+    // (slot*32 + lane)*8 + k is kept at [(slot*8 + k)*32 + lane]: the lanes of a warp, which read the same (slot, k) together and
+    // are 8 channels apart, then hit consecutive words instead of the same banks (see bn_bwd_pm_kernel, gconv_bwd.cu)
+    extern __shared__ __align__(8) float coef[];
+    float2 *coef2 = reinterpret_cast<float2 *>(coef);
+    const bool lane_major = (c & 255) == 0;
     for (int i = threadIdx.x; i < c; i += blockDim.x) {
         const float mean = chan_sum[i] * inv_count;
         const float var = fmaxf(chan_sum[c + i] * inv_count - mean * mean, 0.f);
         const float a = rsqrtf(var + bn_eps) * (gamma ? gamma[i] : 1.f);
-        coef[i] = a;
-        coef[c + i] = (beta ? beta[i] : 0.f) - mean * a;
+        const int at = lane_major ? ((i >> 8) * 8 + (i & 7)) * 32 + ((i >> 3) & 31) : i;
+        coef2[at] = make_float2(a, (beta ? beta[i] : 0.f) - mean * a);
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -541,12 +546,14 @@ __global__ void __launch_bounds__(256) bn_act_pm_kernel(__nv_bfloat16 *y, __nv_b
             for (int i = lane; i < c / 8; i += 32) {
                 uint4 q = row[i];
                 uint32_t *qw = reinterpret_cast<uint32_t *>(&q);
+                const int base = lane_major ? (i >> 5) * 256 + lane : i * 8;  // + k*32 / + k for channel i*8 + k
+                const int kstep = lane_major ? 32 : 1;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     __nv_bfloat162 b2 = *reinterpret_cast<__nv_bfloat162 *>(&qw[j]);
-                    const int ch = i * 8 + 2 * j;
-                    float lo = __low2float(b2) * coef[ch] + coef[c + ch];
-                    float hi = __high2float(b2) * coef[ch + 1] + coef[c + ch + 1];
+                    const float2 c0 = coef2[base + (2 * j) * kstep], c1 = coef2[base + (2 * j + 1) * kstep];
+                    float lo = __low2float(b2) * c0.x + c0.y;
+                    float hi = __high2float(b2) * c1.x + c1.y;
                     if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
                     const uint32_t packed = tc::pack_bf16x2(lo, hi);
                     __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162 *>(&packed);
