@@ -87,7 +87,8 @@ def _conv_eligible(conv):
 class BackboneRun(object):
     """A stretch of the model's `vgg` ModuleList executed in PM/bf16: every [Conv2d, (BatchNorm2d), ReLU] triple whose
     conv fits the tcgen05 kernel runs as one launch with BN folded and ReLU fused (eval mode), MaxPool2d runs on PM, and
-    anything else (conv6: dilation 6) round-trips through torch.  SURVEY §8f rank 1, forward half."""
+    anything else (conv6: dilation 6) round-trips through torch.  SURVEY §8f rank 1, evaluation mode; in training mode the same
+    layers run under autograd as PMConvLayer nodes (run_layers(tc=...))."""
 
     def __init__(self, modules):
         self.modules = list(modules)
@@ -202,7 +203,7 @@ def dgrad_weight(weight, groups):
     """Filter with which the data gradient of a stride-1 'same' convolution is itself such a convolution of dY:
     d/dx conv2d(x, w, padding=k//2, groups=g) . dY == conv2d(dY, dgrad_weight(w, g), padding=k//2, groups=g) —
     rotated by 180 degrees, in / out channels swapped inside each group ([Cout, Cin/g, k, k] -> [Cin, Cout/g, k, k]).
-    Host-side half of the backward planned in DESIGN.md §7: packed with `gssd_conv_pack_weights`, it puts dgrad on the
+    Host-side half of the backward: packed with `gssd_conv_pack_weights`, it puts dgrad on the
     same tcgen05 kernel as the forward."""
     cout, cin_g, kh, kw = weight.shape
     wt = weight.reshape(groups, cout // groups, cin_g, kh, kw).transpose(1, 2).flip(3, 4)
