@@ -631,9 +631,9 @@ class PMConvLayer(object):
         wgrad_ok = (cg % 128 == 0 and (g == 1 or ng % 128 == 0)) or (cg == 64 and g % 2 == 0 and (2 * ng) % 128 == 0)
         if not wgrad_ok or conv.out_channels % 256 or conv.out_channels > 1024:        # gssd_bn_relu_bwd_pm: whole 256-channel rows
             return False
-        # widest feature map whose 3x3 slab ring fits twice beside the weight stages of gssd_conv_igemm (forward and data gradient):
-        # 128-column weight tiles leave room for slabs of up to 64 pixels per row, 64-column tiles for 150
-        w_max = 62 if (ng % 128 == 0 or cg % 128 == 0) else 150
+        # widest feature map whose 3x3 slab ring fits twice beside the weight stages of gssd_conv_igemm (forward and data gradient;
+        # its host-side stage arithmetic gives 61 pixels per row with 128-column weight tiles, 157 with 64-column tiles)
+        w_max = 60 if (ng % 128 == 0 or cg % 128 == 0) else 144
         if width is not None and width > w_max:
             return False
         return x is None or (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
