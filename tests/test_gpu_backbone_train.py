@@ -6,7 +6,6 @@ counts and feature-map sizes of the reference's 300 x 300 model, and the whole t
 keeps those layers on cuDNN."""
 import copy
 import os
-import types
 
 import numpy as np
 import pytest
